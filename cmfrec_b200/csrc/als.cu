@@ -1,0 +1,254 @@
+// See als.h.  Host-side orchestration only; all arithmetic on factor rows happens in the kernels.
+#include "als.h"
+#include "nccl_link.h"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+namespace cmfb200 {
+
+static int long_row_threshold()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = std::getenv("CMFB200_LONG_ROW");
+        v = e ? std::atoi(e) : 2048;
+        if (v < 64) v = 64;
+    }
+    return v;
+}
+
+// Rows are dealt to ranks round-robin in order of decreasing degree, so that every rank gets the same
+// number of rows (equal-sized all-gather blocks) and nearly the same number of stored entries.
+// With one rank the numbering is left untouched.
+static void build_renumbering(const size_t *ptr, int_t rows, int world, Renumbering &ren)
+{
+    ren.block = (rows + world - 1) / world;
+    ren.rows_padded = ren.block * world;
+    ren.to_dev.resize(rows);
+    ren.to_old.assign(ren.rows_padded, -1);
+    if (world == 1) {
+        std::iota(ren.to_dev.begin(), ren.to_dev.end(), 0);
+        std::iota(ren.to_old.begin(), ren.to_old.begin() + rows, 0);
+        return;
+    }
+    std::vector<int_t> by_degree(rows);
+    std::iota(by_degree.begin(), by_degree.end(), 0);
+    std::stable_sort(by_degree.begin(), by_degree.end(), [&](int_t a, int_t b) {
+        return (ptr[a + 1] - ptr[a]) > (ptr[b + 1] - ptr[b]);
+    });
+    for (int_t s = 0; s < rows; s++) {
+        const int_t dev = (s % world) * ren.block + s / world;
+        ren.to_dev[by_degree[s]] = dev;
+        ren.to_old[dev] = by_degree[s];
+    }
+}
+
+static int build_side(const size_t *ptr, const int_t *idx, const real_t *val, const Renumbering &rows_ren,
+                      const Renumbering &cols_ren, int rank, cudaStream_t stream, DeviceSide &side)
+{
+    side.rows_padded = rows_ren.rows_padded;
+    side.block = rows_ren.block;
+    side.row_begin = rank * rows_ren.block;
+    side.row_end = side.row_begin + rows_ren.block;
+    std::vector<size_t> hptr((size_t)side.rows_padded + 1, 0);
+    size_t total = 0;
+    for (int_t r = side.row_begin; r < side.row_end; r++) {
+        const int_t old = rows_ren.to_old[r];
+        if (old >= 0) total += ptr[old + 1] - ptr[old];
+    }
+    std::vector<int_t> hidx(total);
+    std::vector<real_t> hval(total);
+    size_t at = 0;
+    for (int_t r = 0; r < side.rows_padded; r++) {
+        hptr[r] = at;
+        if (r < side.row_begin || r >= side.row_end) continue;
+        const int_t old = rows_ren.to_old[r];
+        if (old < 0) continue;
+        for (size_t e = ptr[old]; e < ptr[old + 1]; e++) {
+            hidx[at] = cols_ren.to_dev[idx[e]];
+            hval[at] = val[e];
+            at++;
+        }
+    }
+    hptr[side.rows_padded] = at;
+    side.nnz_local = total;
+
+    // processing order: local rows by decreasing degree; rows longer than the threshold get a whole block
+    std::vector<int_t> order;
+    order.reserve(side.block);
+    for (int_t r = side.row_begin; r < side.row_end; r++)
+        if (rows_ren.to_old[r] >= 0) order.push_back(r);
+    std::stable_sort(order.begin(), order.end(), [&](int_t a, int_t b) {
+        return (hptr[a + 1] - hptr[a]) > (hptr[b + 1] - hptr[b]);
+    });
+    const size_t thr = (size_t)long_row_threshold();
+    int_t n_long = 0;
+    while (n_long < (int_t)order.size() && hptr[order[n_long] + 1] - hptr[order[n_long]] >= thr) n_long++;
+    side.n_order = (int_t)order.size();
+    side.n_long = n_long;
+
+    if (!side.ptr.alloc(hptr.size()) || !side.idx.alloc(std::max<size_t>(total, 1)) ||
+        !side.val.alloc(std::max<size_t>(total, 1)) || !side.order.alloc(std::max<size_t>(order.size(), 1)))
+        return 1;
+    cudaMemcpyAsync(side.ptr.p, hptr.data(), hptr.size() * sizeof(size_t), cudaMemcpyHostToDevice, stream);
+    if (total) {
+        cudaMemcpyAsync(side.idx.p, hidx.data(), total * sizeof(int_t), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(side.val.p, hval.data(), total * sizeof(real_t), cudaMemcpyHostToDevice, stream);
+    }
+    if (!order.empty())
+        cudaMemcpyAsync(side.order.p, order.data(), order.size() * sizeof(int_t), cudaMemcpyHostToDevice, stream);
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+AlsState::~AlsState() { delete link; }
+
+int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
+                    const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, cudaStream_t s, const void *nccl_id)
+{
+    cfg = c;
+    stream = s;
+    if (cfg.kk < 1 || cfg.kk > max_supported_k()) return 2;
+    if (cfg.world > 1) {
+        if (!nccl_id) return 2;
+        link = new NcclLink();
+        if (link->init(nccl_id, cfg.rank, cfg.world) != 0) return 1;
+    }
+    build_renumbering(csr_p, cfg.m, cfg.world, renA);
+    build_renumbering(csc_p, cfg.n, cfg.world, renB);
+    int rc = build_side(csr_p, csr_i, csr_v, renA, renB, cfg.rank, stream, byA);
+    if (rc) return rc;
+    rc = build_side(csc_p, csc_i, csc_v, renB, renA, cfg.rank, stream, byB);
+    if (rc) return rc;
+    ldA = cmf_ld_for(cfg.kk + 1);
+    ldB = cmf_ld_for(cfg.kk + 1);
+    if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB)) return 1;
+    cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream);
+    cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream);
+    if (cfg.implicit) {
+        if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
+    }
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+static void pack_factor(const real_t *h, int ldh, const real_t *hbias, int_t rows, int kk, const Renumbering &ren, int ld,
+                        std::vector<real_t> &out)
+{
+    out.assign((size_t)ren.rows_padded * ld, real_t(0));
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < (long long)rows; r++) {
+        real_t *dst = out.data() + (size_t)ren.to_dev[r] * ld;
+        std::memcpy(dst, h + (size_t)r * ldh, (size_t)kk * sizeof(real_t));
+        dst[kk] = hbias ? hbias[r] : real_t(0);
+    }
+}
+
+int AlsState::upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb,
+                             const real_t *hbiasB)
+{
+    std::vector<real_t> tmp;
+    pack_factor(hA, lda, hbiasA, cfg.m, cfg.kk, renA, ldA, tmp);
+    if (cudaMemcpyAsync(A.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return 1;
+    cudaStreamSynchronize(stream);
+    pack_factor(hB, ldb, hbiasB, cfg.n, cfg.kk, renB, ldB, tmp);
+    if (cudaMemcpyAsync(B.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+static void unpack_factor(const std::vector<real_t> &in, int ld, const Renumbering &ren, int_t rows, int kk, real_t *h,
+                          int ldh, real_t *hbias)
+{
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < (long long)rows; r++) {
+        const real_t *src = in.data() + (size_t)ren.to_dev[r] * ld;
+        if (h) std::memcpy(h + (size_t)r * ldh, src, (size_t)kk * sizeof(real_t));
+        if (hbias) hbias[r] = src[kk];
+    }
+}
+
+int AlsState::download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB)
+{
+    std::vector<real_t> tmp(A.n);
+    if (cudaMemcpyAsync(tmp.data(), A.p, A.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+    unpack_factor(tmp, ldA, renA, cfg.m, cfg.kk, hA, lda, hbiasA);
+    tmp.resize(B.n);
+    if (cudaMemcpyAsync(tmp.data(), B.p, B.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+    unpack_factor(tmp, ldB, renB, cfg.n, cfg.kk, hB, ldb, hbiasB);
+    return 0;
+}
+
+int AlsState::half_sweep(int which, int iter, int solver)
+{
+    const bool solveA = which == 1;
+    CgSweepParams p{};
+    p.F = solveA ? A.p : B.p;
+    p.ldF = solveA ? ldA : ldB;
+    p.G = solveA ? B.p : A.p;
+    p.ldG = solveA ? ldB : ldA;
+    p.kk = cfg.kk;
+    const DeviceSide &side = solveA ? byA : byB;
+    p.X = side.view();
+    p.plan = side.plan();
+    p.lam = solveA ? cfg.lam_A : cfg.lam_B;
+    p.lam_last = solveA ? cfg.lam_biasA : cfg.lam_biasB;
+    p.scale_lam = cfg.scale_lam;
+    p.scale_bias_const = false;
+    p.max_cg_steps = cfg.max_cg_steps;
+    const bool both = cfg.user_bias && cfg.item_bias;
+    if (cfg.implicit) {
+        p.solve_bias = p.center_opp = p.bias_start_one = false;
+        const int_t opp_rows = solveA ? renB.rows_padded : renA.rows_padded;
+        int rc = launch_gram(p.G, p.ldG, opp_rows, cfg.kk, gram.p, gram_ws.p, stream);
+        launches += 2;
+        if (rc) return rc;
+        p.gram = gram.p;
+    } else {
+        p.solve_bias = solveA ? cfg.user_bias : cfg.item_bias;
+        p.center_opp = solveA ? cfg.item_bias : cfg.user_bias;
+        // Where the reference keeps a 1.0 in the bias column at the moment a row is (re)started:
+        // users: always when both biases are fitted; items: from the second iteration on
+        // (src/collective.c:8538-8542, 8728-8732).
+        p.bias_start_one = both && (solveA || iter > 0);
+    }
+    int rc;
+    if (solver == 0) {
+        rc = cfg.implicit ? launch_implicit_cg_sweep(p, stream) : launch_explicit_cg_sweep(p, stream);
+    } else {
+        rc = cfg.implicit ? launch_implicit_chol_sweep(p, stream) : launch_explicit_chol_sweep(p, stream);
+    }
+    launches += 1;
+    return rc;
+}
+
+int AlsState::exchange(int which)
+{
+    if (cfg.world <= 1) return 0;
+    const bool solveA = which == 1;
+    real_t *F = solveA ? A.p : B.p;
+    const int ld = solveA ? ldA : ldB;
+    const int_t block = solveA ? renA.block : renB.block;
+    launches += 1;
+    return link->all_gather_inplace(F, (size_t)block * ld * sizeof(real_t), stream);
+}
+
+int AlsState::iterate(int first_iter, int n_iters, int niter_total, bool use_cg, bool finalize_chol)
+{
+    for (int it = first_iter; it < first_iter + n_iters; it++) {
+        // the reference switches the last iteration to the exact solver (src/collective.c:8336-8340)
+        const bool cg_now = use_cg && !(finalize_chol && it == niter_total - 1);
+        const int solver = cg_now ? 0 : 1;
+        int rc = half_sweep(0, it, solver);
+        if (rc) return rc;
+        if ((rc = exchange(0))) return rc;
+        if ((rc = half_sweep(1, it, solver))) return rc;
+        if ((rc = exchange(1))) return rc;
+    }
+    return 0;
+}
+
+}  // namespace cmfb200

@@ -1,0 +1,91 @@
+// The ALS alternation on the device: state that lives in HBM for the duration of a fit (both orientations
+// of X, both factor matrices, Gram workspace) and the half-sweep / iteration drivers on top of the kernels
+// in sweep.h.  This is the loop body of the reference's fit_collective_explicit_als
+// (src/collective.c:8334-8898) and fit_collective_implicit_als (src/collective.c:9827-10040) for models
+// without side information.
+#pragma once
+#include <vector>
+#include <cuda_runtime.h>
+#include "cmf_types.h"
+#include "sweep.h"
+
+namespace cmfb200 {
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    bool alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return true;
+        return cudaMalloc((void **)&p, count * sizeof(T)) == cudaSuccess;
+    }
+};
+
+// One orientation of X (CSR = rows are users, CSC = rows are items) restricted to this rank's row block,
+// with row and column ids already renumbered into the device ("dealt") numbering.
+struct DeviceSide {
+    int_t rows_padded = 0;        // world * block
+    int_t block = 0;              // rows per rank
+    int_t row_begin = 0, row_end = 0;
+    size_t nnz_local = 0;
+    DevBuf<size_t> ptr;
+    DevBuf<int_t> idx;
+    DevBuf<real_t> val;
+    DevBuf<int_t> order;
+    int_t n_order = 0, n_long = 0;
+    CsrView view() const { return CsrView{ptr.p, idx.p, val.p}; }
+    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long}; }
+};
+
+struct Renumbering {              // old (caller) row id <-> device row id
+    std::vector<int_t> to_dev;    // [rows]
+    std::vector<int_t> to_old;    // [rows_padded], -1 for padding rows
+    int_t block = 0, rows_padded = 0;
+};
+
+struct AlsConfig {
+    bool implicit = false;
+    int_t m = 0, n = 0, kk = 0;   // kk = k + k_main
+    bool user_bias = false, item_bias = false;
+    real_t lam_A = 0, lam_B = 0;          // regulariser of the factor columns
+    real_t lam_biasA = 0, lam_biasB = 0;  // regulariser of the bias coordinate
+    bool scale_lam = false;
+    int max_cg_steps = 3;
+    int rank = 0, world = 1;
+};
+
+class NcclLink;
+
+class AlsState {
+public:
+    AlsConfig cfg;
+    cudaStream_t stream = nullptr;
+    Renumbering renA, renB;
+    DeviceSide byA, byB;          // byA: rows = users (CSR); byB: rows = items (CSC)
+    int ldA = 0, ldB = 0;
+    DevBuf<real_t> A, B;          // [rows_padded x ld], device numbering
+    DevBuf<real_t> gram, gram_ws;
+    NcclLink *link = nullptr;
+    long long launches = 0;       // kernels launched so far (for bench.py's gpu_launches)
+
+    ~AlsState();
+    // host CSR/CSC in caller numbering (values already centred / scaled as the model requires)
+    int setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v, const size_t *csc_p,
+              const int_t *csc_i, const real_t *csc_v, cudaStream_t s, const void *nccl_id);
+    // factors in caller numbering: A [m x kk] (ld = lda), biasA [m] or null; same for B
+    int upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb, const real_t *hbiasB);
+    int download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB);
+    // which: 0 = update B (items) from A, 1 = update A (users) from B.  `solver`: 0 = CG, 1 = Cholesky
+    int half_sweep(int which, int iter, int solver);
+    int exchange(int which);      // all-gather the freshly solved block (no-op on one GPU)
+    int iterate(int first_iter, int n_iters, int niter_total, bool use_cg, bool finalize_chol);
+};
+
+}  // namespace cmfb200

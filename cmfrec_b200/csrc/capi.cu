@@ -1,0 +1,189 @@
+// extern "C" surface of libcmfrec_b200_{f32,f64}.so -- see include/cmfrec_b200.h.
+// Pure forwarding: argument lists are the reference's (src/cmfrec.h), bodies live in fit.cu, als.cu,
+// host_prep.cpp, popular.cpp and topn.cu.
+#include "../../include/cmfrec_b200.h"
+#include <cstdio>
+#include "als.h"
+#include "fit.h"
+#include "host_prep.h"
+#include "nccl_link.h"
+#include "popular.h"
+#include "topn.h"
+
+using namespace cmfb200;
+
+struct cmfb200_als {
+    AlsState st;
+};
+
+extern "C" {
+
+int fit_collective_explicit_als(
+    real_t *biasA, real_t *biasB, real_t *A, real_t *B, real_t *C, real_t *D, real_t *Ai, real_t *Bi,
+    bool add_implicit_features, bool reset_values, int_t seed, real_t *glob_mean, real_t *U_colmeans,
+    real_t *I_colmeans, int_t m, int_t n, int_t k, int_t ixA[], int_t ixB[], real_t *X, size_t nnz, real_t *Xfull,
+    real_t *weight, bool user_bias, bool item_bias, bool center, real_t lam, real_t *lam_unique, real_t l1_lam,
+    real_t *l1_lam_unique, bool scale_lam, bool scale_lam_sideinfo, bool scale_bias_const, real_t *scaling_biasA,
+    real_t *scaling_biasB, real_t *U, int_t m_u, int_t p, real_t *II, int_t n_i, int_t q, int_t U_row[], int_t U_col[],
+    real_t *U_sp, size_t nnz_U, int_t I_row[], int_t I_col[], real_t *I_sp, size_t nnz_I, bool NA_as_zero_X,
+    bool NA_as_zero_U, bool NA_as_zero_I, int_t k_main, int_t k_user, int_t k_item, real_t w_main, real_t w_user,
+    real_t w_item, real_t w_implicit, int_t niter, int nthreads, bool verbose, bool handle_interrupt, bool use_cg,
+    int_t max_cg_steps, bool precondition_cg, bool finalize_chol, bool nonneg, int_t max_cd_steps, bool nonneg_C,
+    bool nonneg_D, bool precompute_for_predictions, bool include_all_X, real_t *B_plus_bias, real_t *precomputedBtB,
+    real_t *precomputedTransBtBinvBt, real_t *precomputedBtXbias, real_t *precomputedBeTBeChol,
+    real_t *precomputedBiTBi, real_t *precomputedTransCtCinvCt, real_t *precomputedCtCw, real_t *precomputedCtUbias)
+{
+    ExplicitArgs a{biasA, biasB, A, B, C, D, Ai, Bi, add_implicit_features, reset_values, seed, glob_mean, U_colmeans,
+                   I_colmeans, m, n, k, ixA, ixB, X, nnz, Xfull, weight, user_bias, item_bias, center, lam, lam_unique,
+                   l1_lam, l1_lam_unique, scale_lam, scale_lam_sideinfo, scale_bias_const, scaling_biasA,
+                   scaling_biasB, U, m_u, p, II, n_i, q, U_row, U_col, U_sp, nnz_U, I_row, I_col, I_sp, nnz_I,
+                   NA_as_zero_X, NA_as_zero_U, NA_as_zero_I, k_main, k_user, k_item, w_main, w_user, w_item,
+                   w_implicit, niter, nthreads, verbose, handle_interrupt, use_cg, max_cg_steps, precondition_cg,
+                   finalize_chol, nonneg, max_cd_steps, nonneg_C, nonneg_D, precompute_for_predictions, include_all_X,
+                   B_plus_bias, precomputedBtB, precomputedTransBtBinvBt, precomputedBtXbias, precomputedBeTBeChol,
+                   precomputedBiTBi, precomputedTransCtCinvCt, precomputedCtCw, precomputedCtUbias};
+    return fit_explicit(a);
+}
+
+int fit_collective_implicit_als(
+    real_t *A, real_t *B, real_t *C, real_t *D, bool reset_values, int_t seed, real_t *U_colmeans, real_t *I_colmeans,
+    int_t m, int_t n, int_t k, int_t ixA[], int_t ixB[], real_t *X, size_t nnz, real_t lam, real_t *lam_unique,
+    real_t l1_lam, real_t *l1_lam_unique, real_t *U, int_t m_u, int_t p, real_t *II, int_t n_i, int_t q, int_t U_row[],
+    int_t U_col[], real_t *U_sp, size_t nnz_U, int_t I_row[], int_t I_col[], real_t *I_sp, size_t nnz_I,
+    bool NA_as_zero_U, bool NA_as_zero_I, int_t k_main, int_t k_user, int_t k_item, real_t w_main, real_t w_user,
+    real_t w_item, real_t *w_main_multiplier, real_t alpha, bool adjust_weight, bool apply_log_transf, int_t niter,
+    int nthreads, bool verbose, bool handle_interrupt, bool use_cg, int_t max_cg_steps, bool precondition_cg,
+    bool finalize_chol, bool nonneg, int_t max_cd_steps, bool nonneg_C, bool nonneg_D, bool precompute_for_predictions,
+    real_t *precomputedBtB, real_t *precomputedBeTBe, real_t *precomputedBeTBeChol, real_t *precomputedCtUbias)
+{
+    ImplicitArgs a{A, B, C, D, reset_values, seed, U_colmeans, I_colmeans, m, n, k, ixA, ixB, X, nnz, lam, lam_unique,
+                   l1_lam, l1_lam_unique, U, m_u, p, II, n_i, q, U_row, U_col, U_sp, nnz_U, I_row, I_col, I_sp, nnz_I,
+                   NA_as_zero_U, NA_as_zero_I, k_main, k_user, k_item, w_main, w_user, w_item, w_main_multiplier,
+                   alpha, adjust_weight, apply_log_transf, niter, nthreads, verbose, handle_interrupt, use_cg,
+                   max_cg_steps, precondition_cg, finalize_chol, nonneg, max_cd_steps, nonneg_C, nonneg_D,
+                   precompute_for_predictions, precomputedBtB, precomputedBeTBe, precomputedBeTBeChol,
+                   precomputedCtUbias};
+    return fit_implicit(a);
+}
+
+int fit_most_popular(real_t *biasA, real_t *biasB, real_t *glob_mean, real_t lam_user, real_t lam_item, bool scale_lam,
+                     bool scale_bias_const, real_t alpha, int_t m, int_t n, int_t ixA[], int_t ixB[], real_t *X,
+                     size_t nnz, real_t *Xfull, real_t *weight, bool implicit, bool adjust_weight,
+                     bool apply_log_transf, bool nonneg, bool NA_as_zero, real_t *w_main_multiplier, int nthreads)
+{
+    return most_popular(biasA, biasB, glob_mean, lam_user, lam_item, scale_lam, scale_bias_const, alpha, m, n, ixA, ixB,
+                        X, nnz, Xfull, weight, implicit, adjust_weight, apply_log_transf, nonneg, NA_as_zero,
+                        w_main_multiplier, nthreads);
+}
+
+int topN(real_t *a_vec, int_t k_user, real_t *B, int_t k_item, real_t *biasB, real_t glob_mean, real_t biasA, int_t k,
+         int_t k_main, int_t *include_ix, int_t n_include, int_t *exclude_ix, int_t n_exclude, int_t *outp_ix,
+         real_t *outp_score, int_t n_top, int_t n, int nthreads)
+{
+    return top_n(a_vec, k_user, B, k_item, biasB, glob_mean, biasA, k, k_main, include_ix, n_include, exclude_ix,
+                 n_exclude, outp_ix, outp_score, n_top, n, nthreads);
+}
+
+bool get_has_openmp(void)
+{
+#ifdef _OPENMP
+    return true;
+#else
+    return false;
+#endif
+}
+
+const char *cmfb200_real_name(void) { return CMF_REAL_NAME; }
+
+int cmfb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void cmfb200_random_init(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal)
+{
+    random_init(A, sizeA, B, sizeB, seed, normal);
+}
+
+void cmfb200_coo_to_csr_and_csc(const int_t *Xrow, const int_t *Xcol, const real_t *Xval, int_t m, int_t n, size_t nnz,
+                                size_t *csr_p, int_t *csr_i, real_t *csr_v, size_t *csc_p, int_t *csc_i, real_t *csc_v)
+{
+    coo_to_csr_and_csc(Xrow, Xcol, Xval, m, n, nnz, csr_p, csr_i, csr_v, csc_p, csc_i, csc_v);
+}
+
+real_t cmfb200_global_mean(const real_t *X, size_t nnz, int nthreads) { return global_mean(X, nnz, nthreads); }
+
+void cmfb200_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
+                                  const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, real_t lam_user,
+                                  real_t lam_item, bool scale_lam, bool nonneg, real_t *biasA, real_t *biasB,
+                                  int nthreads)
+{
+    init_biases_twosided(m, n, csr_p, csr_i, csr_v, csc_p, csc_i, csc_v, lam_user, lam_item, scale_lam, nonneg, biasA,
+                         biasB, nthreads);
+}
+
+int cmfb200_nccl_unique_id(void *out128) { return NcclLink::unique_id(out128); }
+
+int cmfb200_als_create(cmfb200_als **out, const cmfb200_als_options *opt, const size_t *csr_p, const int_t *csr_i,
+                       const real_t *csr_v, const size_t *csc_p, const int_t *csc_i, const real_t *csc_v)
+{
+    if (!out || !opt) return 2;
+    *out = nullptr;
+    if (cmfb200_device_count() < 1) {
+        std::fprintf(stderr, "cmfrec_b200: no CUDA device available; this library has no CPU path.\n");
+        return 1;
+    }
+    AlsConfig c;
+    c.implicit = opt->implicit != 0;
+    c.m = opt->m; c.n = opt->n; c.kk = opt->k;
+    c.user_bias = !c.implicit && opt->user_bias; c.item_bias = !c.implicit && opt->item_bias;
+    c.lam_A = opt->lam_A; c.lam_B = opt->lam_B; c.lam_biasA = opt->lam_biasA; c.lam_biasB = opt->lam_biasB;
+    c.scale_lam = opt->scale_lam != 0;
+    c.max_cg_steps = opt->max_cg_steps;
+    c.rank = opt->rank; c.world = opt->world < 1 ? 1 : opt->world;
+    cmfb200_als *s = new cmfb200_als();
+    int rc = s->st.setup(c, csr_p, csr_i, csr_v, csc_p, csc_i, csc_v, (cudaStream_t)opt->stream, opt->nccl_id);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return 0;
+}
+
+void cmfb200_als_destroy(cmfb200_als *s) { delete s; }
+
+int cmfb200_als_set_factors(cmfb200_als *s, const real_t *A, const real_t *biasA, const real_t *B, const real_t *biasB)
+{
+    return s->st.upload_factors(A, s->st.cfg.kk, biasA, B, s->st.cfg.kk, biasB);
+}
+
+int cmfb200_als_get_factors(cmfb200_als *s, real_t *A, real_t *biasA, real_t *B, real_t *biasB)
+{
+    return s->st.download_factors(A, s->st.cfg.kk, biasA, B, s->st.cfg.kk, biasB);
+}
+
+int cmfb200_als_half_sweep(cmfb200_als *s, int which, int iter, int solver)
+{
+    int rc = s->st.half_sweep(which, iter, solver);
+    if (rc) return rc;
+    return s->st.exchange(which);
+}
+
+int cmfb200_als_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg, int finalize_chol)
+{
+    return s->st.iterate(first_iter, n_iters, niter_total, use_cg != 0, finalize_chol != 0);
+}
+
+int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }
+
+long long cmfb200_als_launch_count(const cmfb200_als *s) { return s->st.launches; }
+
+void cmfb200_als_local_counts(const cmfb200_als *s, size_t *nnzA, size_t *nnzB, int_t *rowsA, int_t *rowsB)
+{
+    if (nnzA) *nnzA = s->st.byA.nnz_local;
+    if (nnzB) *nnzB = s->st.byB.nnz_local;
+    if (rowsA) *rowsA = s->st.byA.n_order;
+    if (rowsB) *rowsB = s->st.byB.n_order;
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// fit_collective_explicit_als / fit_collective_implicit_als on the GPU, behind the reference's own
+// argument lists (reference src/cmfrec.h:1851-1921; drivers src/collective.c:7263-9370, 9375-10207).
+//
+// What is covered here is the models the BASELINE configurations fit: sparse COO input, missing = unknown,
+// no observation weights, no L1 / non-negativity constraints, no side information (U, I), with or without
+// user/item biases, centring, scale_lam, CG and/or Cholesky per-row solvers, finalize_chol.
+// Argument combinations outside of that are refused loudly (return code 2, message on stderr): there is
+// deliberately no CPU fallback.
+#include "fit.h"
+#include "als.h"
+#include "host_prep.h"
+#include "postfit.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace cmfb200 {
+
+static int refuse(const char *what)
+{
+    std::fprintf(stderr, "cmfrec_b200: %s is not supported by the GPU path (no CPU fallback).\n", what);
+    return 2;
+}
+
+static int cuda_ready()
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        std::fprintf(stderr, "cmfrec_b200: no CUDA device available; this library has no CPU path.\n");
+        return 1;
+    }
+    return 0;
+}
+
+int fit_explicit(const ExplicitArgs &a)
+{
+    if (a.k_user && a.U == nullptr && a.nnz_U == 0) return 2;
+    if (a.k_item && a.II == nullptr && a.nnz_I == 0) return 2;
+    if (a.k_main && a.Xfull == nullptr && a.nnz == 0) return 2;
+    if (a.Xfull) return refuse("dense X (Xfull)");
+    if (a.weight) return refuse("observation weights");
+    if (a.NA_as_zero_X) return refuse("NA_as_zero_X");
+    if (a.U || a.II || a.nnz_U || a.nnz_I) return refuse("side information (U / I)");
+    if (a.add_implicit_features) return refuse("add_implicit_features");
+    if (a.nonneg || a.nonneg_C || a.nonneg_D) return refuse("non-negativity constraints");
+    if (a.l1_lam != 0 || a.l1_lam_unique) return refuse("L1 regularisation");
+    if (a.precondition_cg) return refuse("precondition_cg");
+    if (a.k_user || a.k_item) return refuse("k_user / k_item without side information");
+    if (a.scale_bias_const && (a.scale_lam || a.scale_lam_sideinfo) && (a.user_bias || a.item_bias))
+        return refuse("scale_bias_const");
+    if (!a.reset_values) return refuse("reset_values = false");
+    if (a.m < 1 || a.n < 1 || a.k + a.k_main < 1) return 2;
+    if (int rc = cuda_ready()) return rc;
+
+    const int_t m = a.m, n = a.n;
+    const int kk = a.k + a.k_main;
+    const size_t nnz = a.nnz;
+    const bool has_bias = a.user_bias || a.item_bias;
+    const bool scale_lam = a.scale_lam || a.scale_lam_sideinfo;
+    bool use_cg = a.use_cg;
+    bool finalize_chol = a.finalize_chol && use_cg;
+
+    // regularisation, with w_main folded away (src/collective.c:7497-7521)
+    real_t lam = a.lam;
+    real_t lam_u[6];
+    const bool has_unique = a.lam_unique != nullptr;
+    for (int i = 0; i < 6; i++) lam_u[i] = has_unique ? a.lam_unique[i] : a.lam;
+    if (a.w_main != 1) {
+        lam /= a.w_main;
+        for (int i = 0; i < 6; i++) lam_u[i] /= a.w_main;
+    }
+
+    // centring (src/collective.c:7555-7568 -> src/common.c:3423)
+    real_t glob_mean = 0;
+    std::vector<real_t> Xc(a.X, a.X + nnz);
+    if (a.center) {
+        glob_mean = global_mean(a.X, nnz, a.nthreads);
+        if (glob_mean != 0)
+            for (size_t e = 0; e < nnz; e++) Xc[e] -= glob_mean;
+    }
+    if (a.glob_mean) *a.glob_mean = glob_mean;
+
+    // both orientations of X (src/collective.c:7593 -> src/helpers.c:1375)
+    std::vector<size_t> csr_p((size_t)m + 1), csc_p((size_t)n + 1);
+    std::vector<int_t> csr_i(nnz), csc_i(nnz);
+    std::vector<real_t> csr_v(nnz), csc_v(nnz);
+    coo_to_csr_and_csc(a.ixA, a.ixB, Xc.data(), m, n, nnz, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(),
+                       csc_i.data(), csc_v.data());
+    std::vector<real_t>().swap(Xc);
+
+    // starting biases (src/collective.c:8164-8226)
+    if (has_bias) {
+        if (a.user_bias && a.item_bias) {
+            init_biases_twosided(m, n, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(), csc_i.data(), csc_v.data(),
+                                 lam_u[0], lam_u[1], scale_lam, false, a.biasA, a.biasB, a.nthreads);
+        } else if (a.user_bias) {
+            init_biases_onesided(m, csr_p.data(), csr_v.data(), lam_u[0], scale_lam, false, a.biasA);
+        } else if (use_cg) {
+            init_biases_onesided(n, csc_p.data(), csc_v.data(), lam_u[1], scale_lam, false, a.biasB);
+        }
+    }
+
+    // starting factors: A random, B zero with CG (src/collective.c:8241-8274)
+    const size_t sizeA = (size_t)m * kk, sizeB = (size_t)n * kk;
+    random_init(a.A, sizeA, nullptr, 0, a.seed, true);
+    if (use_cg) std::memset(a.B, 0, sizeB * sizeof(real_t));
+
+    AlsConfig cfg;
+    cfg.implicit = false;
+    cfg.m = m; cfg.n = n; cfg.kk = kk;
+    cfg.user_bias = a.user_bias; cfg.item_bias = a.item_bias;
+    cfg.lam_A = lam_u[2]; cfg.lam_B = lam_u[3];
+    cfg.lam_biasA = a.user_bias ? lam_u[0] : lam_u[2];
+    cfg.lam_biasB = a.item_bias ? lam_u[1] : lam_u[3];
+    cfg.scale_lam = scale_lam;
+    cfg.max_cg_steps = a.max_cg_steps;
+    (void)lam;
+
+    AlsState st;
+    int rc = st.setup(cfg, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(), csc_i.data(), csc_v.data(), nullptr,
+                      nullptr);
+    if (rc) return rc == 2 ? refuse("this value of k") : rc;
+    rc = st.upload_factors(a.A, kk, a.user_bias ? a.biasA : nullptr, a.B, kk, a.item_bias ? a.biasB : nullptr);
+    if (rc) return rc;
+    rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
+    if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    rc = st.download_factors(a.A, kk, a.user_bias ? a.biasA : nullptr, a.B, kk, a.item_bias ? a.biasB : nullptr);
+    if (rc) return rc;
+    if (cudaStreamSynchronize(nullptr) != cudaSuccess) return 1;
+
+    if (a.precompute_for_predictions) {
+        PostfitExplicit pf;
+        pf.B = a.B; pf.biasB = a.item_bias ? a.biasB : nullptr; pf.n = n; pf.kk = kk;
+        pf.user_bias = a.user_bias; pf.item_bias = a.item_bias;
+        pf.lam = lam_u[2]; pf.lam_bias = lam_u[0]; pf.scale_lam = scale_lam;
+        pf.B_plus_bias = a.B_plus_bias; pf.BtB = a.precomputedBtB; pf.TransBtBinvBt = a.precomputedTransBtBinvBt;
+        rc = postfit_explicit(pf);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int fit_implicit(const ImplicitArgs &a)
+{
+    if (a.k_user && a.U == nullptr && a.nnz_U == 0) return 2;
+    if (a.k_item && a.II == nullptr && a.nnz_I == 0) return 2;
+    if (a.U || a.II || a.nnz_U || a.nnz_I) return refuse("side information (U / I)");
+    if (a.nonneg || a.nonneg_C || a.nonneg_D) return refuse("non-negativity constraints");
+    if (a.l1_lam != 0 || a.l1_lam_unique) return refuse("L1 regularisation");
+    if (a.precondition_cg) return refuse("precondition_cg");
+    if (a.k_user || a.k_item) return refuse("k_user / k_item without side information");
+    if (!a.reset_values) return refuse("reset_values = false");
+    if (a.m < 1 || a.n < 1 || a.k + a.k_main < 1) return 2;
+    if (int rc = cuda_ready()) return rc;
+
+    const int_t m = a.m, n = a.n;
+    const int kk = a.k + a.k_main;
+    const size_t nnz = a.nnz;
+    bool use_cg = a.use_cg;
+    const bool finalize_chol = a.finalize_chol && use_cg;
+
+    // value transform (src/collective.c:9578-9599)
+    std::vector<real_t> Xs(a.X, a.X + nnz);
+    if (a.apply_log_transf)
+        for (size_t e = 0; e < nnz; e++) Xs[e] = std::log(Xs[e]);
+    if (a.alpha != 1)
+        for (size_t e = 0; e < nnz; e++) Xs[e] *= a.alpha;
+
+    std::vector<size_t> csr_p((size_t)m + 1), csc_p((size_t)n + 1);
+    std::vector<int_t> csr_i(nnz), csc_i(nnz);
+    std::vector<real_t> csr_v(nnz), csc_v(nnz);
+    coo_to_csr_and_csc(a.ixA, a.ixB, Xs.data(), m, n, nnz, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(),
+                       csc_i.data(), csc_v.data());
+    std::vector<real_t>().swap(Xs);
+
+    // starting point: A uniform (normal for tiny problems), B zero with CG (src/collective.c:9750-9774)
+    random_init(a.A, (size_t)m * kk, nullptr, 0, a.seed, false);
+    if (use_cg) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
+
+    // weight bookkeeping (src/collective.c:9776-9811)
+    real_t w_main = a.w_main;
+    real_t mult = 1;
+    if (a.adjust_weight) {
+        mult = (real_t)((long double)nnz / (long double)((size_t)m * (size_t)n));
+        w_main *= mult;
+    }
+    if (a.w_main_multiplier) *a.w_main_multiplier = mult;
+    real_t lamA = a.lam_unique ? a.lam_unique[2] : a.lam;
+    real_t lamB = a.lam_unique ? a.lam_unique[3] : a.lam;
+    real_t lam_plain = a.lam;
+    if (w_main != 1) { lamA /= w_main; lamB /= w_main; lam_plain /= w_main; }
+
+    AlsConfig cfg;
+    cfg.implicit = true;
+    cfg.m = m; cfg.n = n; cfg.kk = kk;
+    cfg.lam_A = lamA; cfg.lam_B = lamB;
+    cfg.max_cg_steps = a.max_cg_steps;
+
+    AlsState st;
+    int rc = st.setup(cfg, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(), csc_i.data(), csc_v.data(), nullptr,
+                      nullptr);
+    if (rc) return rc == 2 ? refuse("this value of k") : rc;
+    rc = st.upload_factors(a.A, kk, nullptr, a.B, kk, nullptr);
+    if (rc) return rc;
+    rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
+    if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    rc = st.download_factors(a.A, kk, nullptr, a.B, kk, nullptr);
+    if (rc) return rc;
+
+    if (a.precompute_for_predictions && a.precomputedBtB) {
+        // BtB + lam*I (src/collective.c:10057-10074)
+        postfit_implicit(a.B, n, kk, lam_plain, a.precomputedBtB);
+    }
+    return 0;
+}
+
+}  // namespace cmfb200

@@ -1,0 +1,58 @@
+// Device-level half-sweeps: one call updates every row of one factor matrix given the other one.
+// They are what the reference's optimizeA (src/common.c:2742, sparse "Case 4" :3209-3302) and
+// optimizeA_implicit (src/common.c:3305-3421) do with an OpenMP loop over rows.
+//
+// Device layout of a factor matrix F with kk latent coordinates: row-major [rows x ld], ld =
+// cmf_ld_for(kk + 1); columns 0..kk-1 hold the coordinates, column kk (the "bias slot") holds that
+// row's bias (0 when the side has none), remaining columns are zero padding.
+#pragma once
+#include <cuda_runtime.h>
+#include "cmf_types.h"
+
+namespace cmfb200 {
+
+struct CsrView {            // device pointers
+    const size_t *ptr;      // [rows+1]
+    const int_t *idx;       // [nnz]   column = row index into the opposing factor
+    const real_t *val;      // [nnz]
+};
+
+struct SweepPlan {          // device pointers, built once per CSR by build_sweep_plan()
+    const int_t *order;     // rows sorted by decreasing degree (rows without entries excluded)
+    int_t n_rows;           // length of order
+    int_t n_long;           // the first n_long rows of order get one whole thread block each
+};
+
+struct CgSweepParams {
+    real_t *F; int ldF;           // factor being solved (in/out: CG is warm-started)
+    const real_t *G; int ldG;     // opposing factor
+    int kk;                       // shared latent coordinates
+    CsrView X;
+    SweepPlan plan;
+    real_t lam, lam_last;
+    bool scale_lam, scale_bias_const;
+    bool solve_bias;              // the solved row has a bias coordinate (slot kk of F; opposing value is 1)
+    bool center_opp;              // subtract the opposing row's bias slot from every x before use
+    bool bias_start_one;          // start the bias coordinate from 1.0 instead of the stored bias
+    int max_cg_steps;
+    const real_t *gram;           // implicit only: G^T G, [kk x kk] row-major, full symmetric
+};
+
+// returns 0, or 2 when kk is outside the supported range
+int launch_explicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream);
+int launch_implicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream);
+
+// Exact per-row solves (normal equations + Cholesky); same parameter block, `max_cg_steps` and
+// `bias_start_one` only matter for rows without entries.  reference: factors_closed_form sparse branch
+// src/common.c:978-1013 + 1058-1070, factors_implicit_chol src/common.c:2063-2126.
+int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream);
+int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream);
+
+// gram[kk x kk] = G[:, :kk]^T G[:, :kk] over `rows` rows (full symmetric storage);
+// workspace must hold gram_workspace_elems(kk) elements.
+size_t gram_workspace_elems(int kk);
+int launch_gram(const real_t *G, int ldG, int_t rows, int kk, real_t *gram, real_t *workspace, cudaStream_t stream);
+
+int max_supported_k();
+
+}  // namespace cmfb200

@@ -1,0 +1,219 @@
+/* cmfrec_b200 -- C ABI of the B200-native ALS solver.
+ *
+ * Two shared libraries export this same set of symbols, one per floating-point type, exactly like the
+ * reference builds one extension module per type (reference setup.py:389-412):
+ *     libcmfrec_b200_f64.so   real_t = double   (default)
+ *     libcmfrec_b200_f32.so   real_t = float    (compiled with -DUSE_FLOAT)
+ * int_t is a 32-bit int, index pointers of compressed matrices are size_t, all dense matrices are row-major
+ * (reference include/cmfrec.h.in:201-205, src/cmfrec.h:232-305).
+ *
+ * PART 1 are drop-in replacements: same names, same argument lists, same return codes as the reference
+ * (0 = ok, 1 = out of memory / device failure, 2 = invalid or unsupported input, 3 = interrupted); host pointers in,
+ * host pointers out, caller allocates every output.  A build of the reference's Cython shim links against them
+ * unchanged.
+ * PART 2 exposes the device-resident pieces the fits are made of, for callers that keep data in HBM between
+ * calls (multi-GPU drivers, benchmarks, per-function parity tests).  Pointers marked DEVICE are CUDA device
+ * pointers on the current device; everything else is host memory.
+ */
+#ifndef CMFREC_B200_H
+#define CMFREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef USE_FLOAT
+typedef float cmf_real_t;
+#else
+typedef double cmf_real_t;
+#endif
+#ifndef CMFREC_B200_NO_SHORT_TYPES
+#define real_t cmf_real_t
+#define int_t int
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * PART 1 -- reference entry points
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* replaces fit_collective_explicit_als, reference src/cmfrec.h:1851-1892 (body src/collective.c:7263-9370) */
+int_t fit_collective_explicit_als(
+    real_t *biasA, real_t *biasB,
+    real_t *A, real_t *B,
+    real_t *C, real_t *D,
+    real_t *Ai, real_t *Bi,
+    bool add_implicit_features,
+    bool reset_values, int_t seed,
+    real_t *glob_mean,
+    real_t *U_colmeans, real_t *I_colmeans,
+    int_t m, int_t n, int_t k,
+    int_t ixA[], int_t ixB[], real_t *X, size_t nnz,
+    real_t *Xfull,
+    real_t *weight,
+    bool user_bias, bool item_bias, bool center,
+    real_t lam, real_t *lam_unique,
+    real_t l1_lam, real_t *l1_lam_unique,
+    bool scale_lam, bool scale_lam_sideinfo, bool scale_bias_const,
+    real_t *scaling_biasA, real_t *scaling_biasB,
+    real_t *U, int_t m_u, int_t p,
+    real_t *II, int_t n_i, int_t q,
+    int_t U_row[], int_t U_col[], real_t *U_sp, size_t nnz_U,
+    int_t I_row[], int_t I_col[], real_t *I_sp, size_t nnz_I,
+    bool NA_as_zero_X, bool NA_as_zero_U, bool NA_as_zero_I,
+    int_t k_main, int_t k_user, int_t k_item,
+    real_t w_main, real_t w_user, real_t w_item, real_t w_implicit,
+    int_t niter, int nthreads,
+    bool verbose, bool handle_interrupt,
+    bool use_cg, int_t max_cg_steps, bool precondition_cg, bool finalize_chol,
+    bool nonneg, int_t max_cd_steps, bool nonneg_C, bool nonneg_D,
+    bool precompute_for_predictions,
+    bool include_all_X,
+    real_t *B_plus_bias,
+    real_t *precomputedBtB,
+    real_t *precomputedTransBtBinvBt,
+    real_t *precomputedBtXbias,
+    real_t *precomputedBeTBeChol,
+    real_t *precomputedBiTBi,
+    real_t *precomputedTransCtCinvCt,
+    real_t *precomputedCtCw,
+    real_t *precomputedCtUbias);
+
+/* replaces fit_collective_implicit_als, reference src/cmfrec.h:1893-1921 (body src/collective.c:9375-10207) */
+int_t fit_collective_implicit_als(
+    real_t *A, real_t *B,
+    real_t *C, real_t *D,
+    bool reset_values, int_t seed,
+    real_t *U_colmeans, real_t *I_colmeans,
+    int_t m, int_t n, int_t k,
+    int_t ixA[], int_t ixB[], real_t *X, size_t nnz,
+    real_t lam, real_t *lam_unique,
+    real_t l1_lam, real_t *l1_lam_unique,
+    real_t *U, int_t m_u, int_t p,
+    real_t *II, int_t n_i, int_t q,
+    int_t U_row[], int_t U_col[], real_t *U_sp, size_t nnz_U,
+    int_t I_row[], int_t I_col[], real_t *I_sp, size_t nnz_I,
+    bool NA_as_zero_U, bool NA_as_zero_I,
+    int_t k_main, int_t k_user, int_t k_item,
+    real_t w_main, real_t w_user, real_t w_item,
+    real_t *w_main_multiplier,
+    real_t alpha, bool adjust_weight, bool apply_log_transf,
+    int_t niter, int nthreads,
+    bool verbose, bool handle_interrupt,
+    bool use_cg, int_t max_cg_steps, bool precondition_cg, bool finalize_chol,
+    bool nonneg, int_t max_cd_steps, bool nonneg_C, bool nonneg_D,
+    bool precompute_for_predictions,
+    real_t *precomputedBtB,
+    real_t *precomputedBeTBe,
+    real_t *precomputedBeTBeChol,
+    real_t *precomputedCtUbias);
+
+/* replaces fit_most_popular, reference src/cmfrec.h:1164-1179 (body src/common.c:5371-5699) */
+int_t fit_most_popular(
+    real_t *biasA, real_t *biasB,
+    real_t *glob_mean,
+    real_t lam_user, real_t lam_item,
+    bool scale_lam, bool scale_bias_const,
+    real_t alpha,
+    int_t m, int_t n,
+    int_t ixA[], int_t ixB[], real_t *X, size_t nnz,
+    real_t *Xfull,
+    real_t *weight,
+    bool implicit, bool adjust_weight, bool apply_log_transf,
+    bool nonneg, bool NA_as_zero,
+    real_t *w_main_multiplier,
+    int nthreads);
+
+/* replaces topN, reference src/cmfrec.h:1152-1163 (body src/common.c:5127-5369) */
+int_t topN(
+    real_t *a_vec, int_t k_user,
+    real_t *B, int_t k_item,
+    real_t *biasB,
+    real_t glob_mean, real_t biasA,
+    int_t k, int_t k_main,
+    int_t *include_ix, int_t n_include,
+    int_t *exclude_ix, int_t n_exclude,
+    int_t *outp_ix, real_t *outp_score,
+    int_t n_top, int_t n, int nthreads);
+
+/* replaces get_has_openmp, reference src/cmfrec.h:646 (helpers.c:1817) */
+bool get_has_openmp(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * PART 2 -- building blocks (cmfb200_ prefix)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* "f32" or "f64": which real_t this library was built for */
+const char *cmfb200_real_name(void);
+/* number of CUDA devices visible (0 = none: every compute entry point then fails with code 1) */
+int cmfb200_device_count(void);
+
+/* --- host-side preparation, bit-exact counterparts of reference helpers --------------------------------- */
+/* random_parallel, reference src/helpers.c:930-1043 (A from the seed state, B from the jumped state) */
+void cmfb200_random_init(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal);
+/* coo_to_csr_and_csc, reference src/helpers.c:1375-1491 (no weights) */
+void cmfb200_coo_to_csr_and_csc(const int_t *Xrow, const int_t *Xcol, const real_t *Xval, int_t m, int_t n, size_t nnz,
+                                size_t *csr_p, int_t *csr_i, real_t *csr_v,
+                                size_t *csc_p, int_t *csc_i, real_t *csc_v);
+/* the mean step of calc_mean_and_center, reference src/common.c:3494-3513 + 3603-3604 (sparse, unweighted) */
+real_t cmfb200_global_mean(const real_t *X, size_t nnz, int nthreads);
+/* initialize_biases_twosided, reference src/common.c:4410 (sparse branches :4643-4669, :4799-4825) */
+void cmfb200_init_biases_twosided(int_t m, int_t n,
+                                  const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
+                                  const size_t *csc_p, const int_t *csc_i, const real_t *csc_v,
+                                  real_t lam_user, real_t lam_item, bool scale_lam, bool nonneg,
+                                  real_t *biasA, real_t *biasB, int nthreads);
+
+/* --- device-resident ALS state ---------------------------------------------------------------------------
+ * Holds both orientations of X, both factor matrices and workspaces in HBM.  One state per GPU/process; with
+ * world > 1 every rank passes the same matrices, keeps only its own block of rows of each orientation, and the
+ * freshly solved blocks are all-gathered over NCCL after every half-sweep.                                   */
+typedef struct cmfb200_als cmfb200_als;
+
+typedef struct cmfb200_als_options {
+    int implicit;              /* 0: explicit-feedback model (optimizeA), 1: implicit (optimizeA_implicit) */
+    int_t m, n, k;             /* k = number of latent coordinates solved (reference k + k_main) */
+    int user_bias, item_bias;  /* explicit only */
+    real_t lam_A, lam_B;       /* regulariser for rows of A / rows of B (after division by w_main) */
+    real_t lam_biasA, lam_biasB;
+    int scale_lam;
+    int max_cg_steps;
+    int rank, world;           /* world > 1 needs nccl_id */
+    const void *nccl_id;       /* 128 bytes from cmfb200_nccl_unique_id, identical on all ranks */
+    void *stream;              /* cudaStream_t to enqueue on (NULL = default stream) */
+} cmfb200_als_options;
+
+int cmfb200_nccl_unique_id(void *out128);
+
+/* X given as CSR and CSC with identical entries (values already centred / scaled the way the model wants) */
+int cmfb200_als_create(cmfb200_als **out, const cmfb200_als_options *opt,
+                       const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
+                       const size_t *csc_p, const int_t *csc_i, const real_t *csc_v);
+void cmfb200_als_destroy(cmfb200_als *s);
+/* factors in caller numbering, row-major [m x k] / [n x k]; bias arrays may be NULL */
+int cmfb200_als_set_factors(cmfb200_als *s, const real_t *A, const real_t *biasA, const real_t *B, const real_t *biasB);
+int cmfb200_als_get_factors(cmfb200_als *s, real_t *A, real_t *biasA, real_t *B, real_t *biasB);
+/* one half-sweep: which = 0 updates B from A (reference optimizeA on the CSC), 1 updates A from B.
+ * `iter` is the 0-based ALS iteration (decides the bias warm start, reference src/collective.c:8538-8545).
+ * solver: 0 = conjugate gradient, 1 = Cholesky.  Enqueues on the state's stream; includes the all-gather. */
+int cmfb200_als_half_sweep(cmfb200_als *s, int which, int iter, int solver);
+/* n_iters full iterations (B then A), the last one of `niter_total` switched to Cholesky when finalize_chol */
+int cmfb200_als_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg, int finalize_chol);
+int cmfb200_als_sync(cmfb200_als *s);
+/* kernels launched by this state so far */
+long long cmfb200_als_launch_count(const cmfb200_als *s);
+/* stored entries / rows held by this rank (for throughput accounting) */
+void cmfb200_als_local_counts(const cmfb200_als *s, size_t *nnz_rows_A, size_t *nnz_rows_B, int_t *rows_A, int_t *rows_B);
+
+#ifndef CMFREC_B200_NO_SHORT_TYPES
+#undef real_t
+#undef int_t
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMFREC_B200_H */
