@@ -174,6 +174,23 @@ int cmfb200_als_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_t
     return s->st.iterate(first_iter, n_iters, niter_total, use_cg != 0, finalize_chol != 0);
 }
 
+int cmfb200_als_timed_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg,
+                              int finalize_chol, float *elapsed_ms)
+{
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return 1;
+    cudaEventRecord(e0, s->st.stream);
+    int rc = s->st.iterate(first_iter, n_iters, niter_total, use_cg != 0, finalize_chol != 0);
+    cudaEventRecord(e1, s->st.stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) rc = rc ? rc : 1;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
 int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }
 
 long long cmfb200_als_launch_count(const cmfb200_als *s) { return s->st.launches; }

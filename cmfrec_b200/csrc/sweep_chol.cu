@@ -1,5 +1,253 @@
+// Exact half-sweeps: per row, build the normal equations from the row's stored entries and solve them with a
+// Cholesky factorisation, all inside one thread block.
+//
+//   explicit:  M = sum_e g_e g_e^T + diag(lam .. lam, lam_last),  rhs = sum_e x_e g_e      (g_e = opposing row,
+//              extended by a 1 when the solved side has a bias; x_e already reduced by the opposing bias)
+//              reference factors_closed_form, sparse branch, src/common.c:978-1013 + 1058-1070
+//   implicit:  M = G^T G + lam I + sum_e x_e g_e g_e^T,            rhs = sum_e (x_e + 1) g_e
+//              reference factors_implicit_chol src/common.c:2063-2126 (G^T G + lam I prepared by
+//              optimizeA_implicit src/common.c:3328-3335)
+//
+// The kd x kd matrix (kd = k [+1]) is accumulated in registers as 4x4 tiles of its upper triangle, spread over
+// the 256 threads of the block (each stored entry is staged once in shared memory, 16 at a time, and read by
+// every thread), then written to shared memory and factorised there (right-looking, two barriers per column);
+// the two triangular solves are done by one warp.  Rows without entries are left as the reference leaves them.
 #include "sweep.h"
+#include "device_utils.cuh"
+
 namespace cmfb200 {
-int launch_explicit_chol_sweep(const CgSweepParams &, cudaStream_t) { return 2; }
-int launch_implicit_chol_sweep(const CgSweepParams &, cudaStream_t) { return 2; }
+
+namespace {
+
+constexpr int NT = 256;      // threads per block
+constexpr int NB = 16;       // stored entries staged per round
+
+template <typename T, int TPT, bool IMPLICIT>
+__global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, int kd, int kdp, int ntile_rows)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *M = reinterpret_cast<T *>(smem_raw);          // [kd][kdp]   (kdp = padded row length)
+    T *gs = M + (size_t)kd * kdp;                    // [NB][kdp]   staged opposing rows
+    T *wgt = gs + NB * kdp;                          // [NB]        matrix weight of each staged entry
+    T *xr = wgt + NB;                                // [NB]        right-hand-side weight
+    T *rhs = xr + NB;                                // [kdp]
+    T *colbuf = rhs + kdp;                           // [kdp]       current column of L
+    T *diag = colbuf + kdp;                          // [kdp]       diagonal of L
+    unsigned short *tile_map = reinterpret_cast<unsigned short *>(diag + kdp);   // [ntiles][2]
+
+    const int tid = threadIdx.x;
+    const int kk = p.kk;
+    const bool hb = !IMPLICIT && p.solve_bias;
+    const int ntiles = ntile_rows * (ntile_rows + 1) / 2;
+    for (int t = tid; t < ntiles; t += NT) {
+        int ti = 0, rem = t;
+        while (rem >= ntile_rows - ti) { rem -= ntile_rows - ti; ti++; }
+        tile_map[2 * t] = (unsigned short)ti;
+        tile_map[2 * t + 1] = (unsigned short)(ti + rem);
+    }
+    __syncthreads();
+    int my_ti[TPT], my_tj[TPT];
+#pragma unroll
+    for (int s = 0; s < TPT; s++) {
+        const int t = tid + s * NT;
+        my_ti[s] = t < ntiles ? tile_map[2 * t] : -1;
+        my_tj[s] = t < ntiles ? tile_map[2 * t + 1] : 0;
+    }
+
+    for (int slot = blockIdx.x; slot < p.plan.n_rows; slot += gridDim.x) {
+        const int row = p.plan.order[slot];
+        const size_t beg = p.X.ptr[row];
+        const int nnz = (int)(p.X.ptr[row + 1] - beg);
+        T *frow = p.F + (size_t)row * (size_t)p.ldF;
+        if (nnz <= 0) {
+            if (IMPLICIT) {
+                for (int c = tid; c < kk; c += NT) frow[c] = T(0);       // A := 0 up front (src/common.c:3334)
+            } else if (hb && p.bias_start_one && tid == 0) {
+                frow[kk] = T(1);                                         // see sweep_cg.cu
+            }
+            continue;
+        }
+        T lam = p.lam, lam_last = p.lam_last;
+        if (!IMPLICIT && p.scale_lam) {
+            lam *= (T)nnz;
+            if (!p.scale_bias_const) lam_last *= (T)nnz;
+        }
+
+        T acc[TPT][4][4];
+#pragma unroll
+        for (int s = 0; s < TPT; s++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[s][i][j] = T(0);
+        T rhs_acc = T(0);
+
+        for (int e0 = 0; e0 < nnz; e0 += NB) {
+            const int nb = min(NB, nnz - e0);
+            // ---- stage nb opposing rows (coalesced along the row)
+            if (tid < nb) {
+                const int col = p.X.idx[beg + e0 + tid];
+                const T x = p.X.val[beg + e0 + tid];
+                if (IMPLICIT) {
+                    wgt[tid] = x;
+                    xr[tid] = x + T(1);
+                } else {
+                    const T ob = p.center_opp ? __ldg(p.G + (size_t)col * p.ldG + kk) : T(0);
+                    wgt[tid] = T(1);
+                    xr[tid] = x - ob;
+                }
+            }
+            for (int i = tid; i < nb * kdp; i += NT) {
+                const int b = i / kdp, c = i - b * kdp;
+                const int col = p.X.idx[beg + e0 + b];
+                T v = T(0);
+                if (c < kk) v = __ldg(p.G + (size_t)col * p.ldG + c);
+                else if (c == kk && hb) v = T(1);
+                gs[i] = v;
+            }
+            __syncthreads();
+            // ---- rank-nb update of the register tiles and of the right-hand side
+            for (int b = 0; b < nb; b++) {
+                const T *g = gs + b * kdp;
+                const T wb = wgt[b];
+#pragma unroll
+                for (int s = 0; s < TPT; s++) {
+                    if (my_ti[s] >= 0) {
+                        T gi[4], gj[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) gi[i] = g[4 * my_ti[s] + i];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) gj[j] = g[4 * my_tj[s] + j];
+                        if (IMPLICIT) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) gi[i] *= wb;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[s][i][j] = fma(gi[i], gj[j], acc[s][i][j]);
+                    }
+                }
+                if (tid < kd) rhs_acc = fma(xr[b], g[tid], rhs_acc);
+            }
+            __syncthreads();
+        }
+
+        // ---- assemble M (full symmetric) in shared memory
+#pragma unroll
+        for (int s = 0; s < TPT; s++) {
+            if (my_ti[s] >= 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int a = 4 * my_ti[s] + i, b = 4 * my_tj[s] + j;
+                        if (a < kd && b < kd) {
+                            T v = acc[s][i][j];
+                            if (IMPLICIT) v += p.gram[(size_t)a * kk + b];
+                            if (a == b) v += (hb && a == kd - 1) ? lam_last : lam;
+                            if (a <= b) {
+                                M[b * kdp + a] = v;   // lower triangle is what the factorisation uses
+                                if (my_ti[s] != my_tj[s] || a != b) M[a * kdp + b] = v;
+                            }
+                        }
+                    }
+            }
+        }
+        if (tid < kd) rhs[tid] = rhs_acc;
+        __syncthreads();
+
+        // ---- Cholesky, lower, right-looking
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int j = 0; j < kd; j++) {
+            const T d = sqrt(M[j * kdp + j]);
+            const T inv = T(1) / d;
+            for (int i = j + 1 + tid; i < kd; i += NT) colbuf[i] = M[i * kdp + j] * inv;
+            if (tid == 0) diag[j] = d;
+            __syncthreads();
+            for (int i = j + 1 + warp; i < kd; i += NT / 32) {
+                const T lij = colbuf[i];
+                for (int c = j + 1 + lane; c <= i; c += 32) M[i * kdp + c] = fma(-lij, colbuf[c], M[i * kdp + c]);
+                if (lane == 0) M[i * kdp + j] = lij;
+            }
+            __syncthreads();
+        }
+
+        // ---- L y = rhs, L^T a = y  (one warp; lane owns entries lane, lane+32, ...)
+        if (warp == 0) {
+            for (int j = 0; j < kd; j++) {
+                T yj = rhs[j] / diag[j];
+                __syncwarp();
+                if (lane == 0) rhs[j] = yj;
+                for (int i = j + 1 + lane; i < kd; i += 32) rhs[i] = fma(-M[i * kdp + j], yj, rhs[i]);
+                __syncwarp();
+            }
+            for (int j = kd - 1; j >= 0; j--) {
+                T aj = rhs[j] / diag[j];
+                __syncwarp();
+                if (lane == 0) rhs[j] = aj;
+                for (int i = lane; i < j; i += 32) rhs[i] = fma(-M[j * kdp + i], aj, rhs[i]);
+                __syncwarp();
+            }
+            for (int c = lane; c < kd; c += 32) {
+                if (c < kk) frow[c] = rhs[c];
+                else frow[kk] = rhs[c];
+            }
+        }
+        __syncthreads();
+    }
 }
+
+template <typename T> size_t chol_smem_bytes(int kd, int kdp, int ntile_rows)
+{
+    const size_t ntiles = (size_t)ntile_rows * (ntile_rows + 1) / 2;
+    return ((size_t)kd * kdp + (size_t)NB * kdp + 2 * NB + 3 * (size_t)kdp) * sizeof(T) + ntiles * 2 * sizeof(unsigned short) + 16;
+}
+
+template <typename T, int TPT, bool IMPLICIT>
+int launch_tpt(const CgSweepParams &p, int kd, int kdp, int ntile_rows, cudaStream_t stream)
+{
+    const size_t smem = chol_smem_bytes<T>(kd, kdp, ntile_rows);
+    auto kern = chol_sweep_kernel<T, TPT, IMPLICIT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 2;
+    }
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (occ < 1) return 2;
+    long long grid = (long long)sms * occ;
+    if (grid > p.plan.n_rows) grid = p.plan.n_rows;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, NT, smem, stream>>>(p, kd, kdp, ntile_rows);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+template <bool IMPLICIT> int dispatch_chol(const CgSweepParams &p, cudaStream_t stream)
+{
+    typedef real_t T;
+    const int kd = p.kk + ((!IMPLICIT && p.solve_bias) ? 1 : 0);
+    const int ntile_rows = (kd + 3) / 4;
+    int kdp = ntile_rows * 4;
+    if ((kdp & 31) == 0) kdp += 4;   // keep consecutive rows of M off the same banks
+    const int ntiles = ntile_rows * (ntile_rows + 1) / 2;
+    const int tpt = (ntiles + NT - 1) / NT;
+    if (chol_smem_bytes<T>(kd, kdp, ntile_rows) > 227 * 1024) return 2;
+    if (tpt <= 1) return launch_tpt<T, 1, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+    if (tpt <= 2) return launch_tpt<T, 2, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+    if (tpt <= 3) return launch_tpt<T, 3, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+    if (tpt <= 4) return launch_tpt<T, 4, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+#ifdef USE_FLOAT
+    if (tpt <= 7) return launch_tpt<T, 7, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+#endif
+    return 2;
+}
+
+}  // namespace
+
+int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch_chol<false>(p, stream); }
+int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch_chol<true>(p, stream); }
+
+}  // namespace cmfb200

@@ -202,6 +202,9 @@ int cmfb200_als_get_factors(cmfb200_als *s, real_t *A, real_t *biasA, real_t *B,
 int cmfb200_als_half_sweep(cmfb200_als *s, int which, int iter, int solver);
 /* n_iters full iterations (B then A), the last one of `niter_total` switched to Cholesky when finalize_chol */
 int cmfb200_als_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg, int finalize_chol);
+/* same, bracketed by CUDA events recorded on the state's stream; *elapsed_ms = device time of the n_iters */
+int cmfb200_als_timed_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg,
+                              int finalize_chol, float *elapsed_ms);
 int cmfb200_als_sync(cmfb200_als *s);
 /* kernels launched by this state so far */
 long long cmfb200_als_launch_count(const cmfb200_als *s);

@@ -1,0 +1,202 @@
+"""Shared helpers for the parity tests: synthetic inputs, and thin callers that drive the product library
+and the reference build (oracle/_ref) through the SAME ctypes argument lists."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from refload import ptr, ref  # noqa: E402,F401
+
+
+def synth_coo(m, n, nnz, dtype, seed=0, kind="ratings", dedup=True, zipf=True):
+    """Random COO triplets, sorted by (row, col).  kind: 'ratings' (0.5..5.0) or 'counts' (>=1)."""
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, m, size=nnz)
+    if zipf:
+        w = 1.0 / np.arange(1, n + 1) ** 0.8
+        cols = rng.choice(n, size=nnz, p=w / w.sum())
+        cols = rng.permutation(n)[cols]
+    else:
+        cols = rng.integers(0, n, size=nnz)
+    if dedup:
+        key = np.unique(rows.astype(np.int64) * n + cols)
+        rows, cols = key // n, key % n
+    else:
+        o = np.lexsort((cols, rows))
+        rows, cols = rows[o], cols[o]
+    if kind == "ratings":
+        vals = rng.integers(1, 11, size=rows.size) * 0.5
+    else:
+        vals = np.ceil(rng.lognormal(1.0, 1.5, size=rows.size))
+    return rows.astype(np.int32), cols.astype(np.int32), vals.astype(dtype)
+
+
+def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, item_bias=True, center=True,
+                 scale_lam=False, niter=3, use_cg=True, max_cg_steps=3, finalize_chol=False, seed=1, nthreads=4,
+                 w_main=1.0, lam_unique=None, precompute=False, k_main=0):
+    """Call fit_collective_explicit_als (reference src/cmfrec.h:1851) on `lib`; returns dict of outputs."""
+    dt = np.dtype(dtype)
+    kk = k + k_main
+    A = np.zeros((m, kk), dt)
+    B = np.zeros((n, kk), dt)
+    biasA = np.zeros(m, dt)
+    biasB = np.zeros(n, dt)
+    glob_mean = np.zeros(1, dt)
+    sA = np.zeros(1, dt)
+    sB = np.zeros(1, dt)
+    lu = None if lam_unique is None else np.asarray(lam_unique, dt)
+    ub = int(user_bias)
+    has_bias = user_bias or item_bias
+    Bpb = np.zeros((n, kk + 1), dt) if (precompute and has_bias) else None
+    BtB = np.zeros((kk + ub, kk + ub), dt) if precompute else None
+    TBt = np.zeros((n, kk + ub), dt) if precompute else None
+    ixA = np.ascontiguousarray(ixA, np.int32).copy()
+    ixB = np.ascontiguousarray(ixB, np.int32).copy()
+    X = np.ascontiguousarray(X, dt).copy()
+    rc = lib.fit_collective_explicit_als(
+        ptr(biasA) if user_bias else None, ptr(biasB) if item_bias else None, ptr(A), ptr(B), None, None, None, None,
+        False, True, seed, ptr(glob_mean), None, None, m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size, None, None,
+        user_bias, item_bias, center, lam, ptr(lu), 0.0, None, scale_lam, False, False, ptr(sA), ptr(sB),
+        None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False, False,
+        k_main, 0, 0, w_main, 1.0, 1.0, 1.0, niter, nthreads, False, False, use_cg, max_cg_steps, False, finalize_chol,
+        False, 100, False, False, precompute, True, ptr(Bpb), ptr(BtB), ptr(TBt), None, None, None, None, None, None)
+    return dict(rc=rc, A=A, B=B, biasA=biasA, biasB=biasB, glob_mean=glob_mean[0], B_plus_bias=Bpb, BtB=BtB,
+                TransBtBinvBt=TBt)
+
+
+def fit_implicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=5.0, alpha=1.0, niter=3, use_cg=True, max_cg_steps=3,
+                 finalize_chol=False, seed=1, nthreads=4, w_main=1.0, adjust_weight=False, apply_log_transf=False,
+                 precompute=False, k_main=0):
+    """Call fit_collective_implicit_als (reference src/cmfrec.h:1893) on `lib`."""
+    dt = np.dtype(dtype)
+    kk = k + k_main
+    A = np.zeros((m, kk), dt)
+    B = np.zeros((n, kk), dt)
+    wmm = np.zeros(1, dt)
+    BtB = np.zeros((kk, kk), dt) if precompute else None
+    ixA = np.ascontiguousarray(ixA, np.int32).copy()
+    ixB = np.ascontiguousarray(ixB, np.int32).copy()
+    X = np.ascontiguousarray(X, dt).copy()
+    rc = lib.fit_collective_implicit_als(
+        ptr(A), ptr(B), None, None, True, seed, None, None, m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size,
+        lam, None, 0.0, None, None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False,
+        k_main, 0, 0, w_main, 1.0, 1.0, ptr(wmm), alpha, adjust_weight, apply_log_transf, niter, nthreads,
+        False, False, use_cg, max_cg_steps, False, finalize_chol, False, 100, False, False, precompute,
+        ptr(BtB), None, None, None)
+    return dict(rc=rc, A=A, B=B, w_main_multiplier=wmm[0], BtB=BtB)
+
+
+def csr_csc(lib, dtype, ixA, ixB, X, m, n):
+    """COO -> (csr_p, csr_i, csr_v, csc_p, csc_i, csc_v) through the product's host routine."""
+    dt = np.dtype(dtype)
+    nnz = X.size
+    out = (np.zeros(m + 1, np.uint64), np.zeros(nnz, np.int32), np.zeros(nnz, dt),
+           np.zeros(n + 1, np.uint64), np.zeros(nnz, np.int32), np.zeros(nnz, dt))
+    lib.cmfb200_coo_to_csr_and_csc(ptr(ixA), ptr(ixB), ptr(X), m, n, nnz, *[ptr(t) for t in out])
+    return out
+
+
+def ref_optimizeA(R, dtype, A, B, ptr_, idx, val, *, lam, lam_last, scale_lam, use_cg, max_cg_steps, nthreads=4):
+    """reference optimizeA (src/common.c:2742) on sparse X, missing-as-unknown: updates A [m x k'] in place."""
+    dt = np.dtype(dtype)
+    m, kd = A.shape
+    n = B.shape[0]
+    assert B.shape[1] == kd
+    buf = np.zeros(nthreads * (kd * kd + 8 * kd) + 16, dt)
+    filled = C.c_bool(False)
+    R.optimizeA(ptr(A), kd, ptr(B), kd, m, n, kd, ptr(ptr_), ptr(idx), ptr(val), None, 0, False, False, False,
+                None, None, False, lam, lam_last, 0.0, 0.0, scale_lam, False, None, False, nthreads, False,
+                use_cg, False, max_cg_steps, False, 0, None, None, None, 0.0, None, 1.0, False, None,
+                C.byref(filled), ptr(buf), None)
+
+
+def ref_optimizeA_implicit(R, dtype, A, B, ptr_, idx, val, *, lam, use_cg, max_cg_steps, nthreads=4):
+    """reference optimizeA_implicit (src/common.c:3305): updates A [m x k] in place."""
+    dt = np.dtype(dtype)
+    m, k = A.shape
+    n = B.shape[0]
+    buf = np.zeros(k * k + nthreads * (k * k + 8 * k) + 16, dt)
+    R.optimizeA_implicit(ptr(A), k, ptr(B), k, m, n, k, ptr(ptr_), ptr(idx), ptr(val), lam, 0.0, nthreads, False,
+                         use_cg, False, max_cg_steps, False, 0, None, ptr(buf), None)
+
+
+class AlsSession:
+    """Context manager around cmfb200_als_* (include/cmfrec_b200.h PART 2)."""
+
+    def __init__(self, lib, dtype, csr, csc, m, n, k, *, implicit, user_bias=False, item_bias=False, lam_A=0.0,
+                 lam_B=0.0, lam_biasA=None, lam_biasB=None, scale_lam=False, max_cg_steps=3):
+        self.lib, self.dt = lib, np.dtype(dtype)
+        self.m, self.n, self.k = m, n, k
+        opt = lib.AlsOptions()
+        opt.implicit = int(implicit)
+        opt.m, opt.n, opt.k = m, n, k
+        opt.user_bias, opt.item_bias = int(user_bias), int(item_bias)
+        opt.lam_A, opt.lam_B = lam_A, lam_B
+        opt.lam_biasA = lam_A if lam_biasA is None else lam_biasA
+        opt.lam_biasB = lam_B if lam_biasB is None else lam_biasB
+        opt.scale_lam = int(scale_lam)
+        opt.max_cg_steps = max_cg_steps
+        opt.rank, opt.world = 0, 1
+        opt.nccl_id = None
+        opt.stream = None
+        self.h = C.c_void_p()
+        rc = lib.cmfb200_als_create(C.byref(self.h), C.byref(opt), *[ptr(t) for t in csr], *[ptr(t) for t in csc])
+        if rc:
+            raise RuntimeError("cmfb200_als_create failed with code %d" % rc)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.lib.cmfb200_als_destroy(self.h)
+        self.h = None
+
+    def set_factors(self, A, biasA, B, biasB):
+        rc = self.lib.cmfb200_als_set_factors(self.h, ptr(A), ptr(biasA), ptr(B), ptr(biasB))
+        assert rc == 0, rc
+
+    def get_factors(self, with_bias=False):
+        A = np.zeros((self.m, self.k), self.dt)
+        B = np.zeros((self.n, self.k), self.dt)
+        bA = np.zeros(self.m, self.dt)
+        bB = np.zeros(self.n, self.dt)
+        rc = self.lib.cmfb200_als_get_factors(self.h, ptr(A), ptr(bA), ptr(B), ptr(bB))
+        assert rc == 0, rc
+        return (A, bA, B, bB) if with_bias else (A, B)
+
+    def half_sweep(self, which, it, solver):
+        rc = self.lib.cmfb200_als_half_sweep(self.h, which, it, solver)
+        assert rc == 0, rc
+        assert self.lib.cmfb200_als_sync(self.h) == 0
+
+
+def rel_err(x, y):
+    """max |x - y| / max |y| (the form the parity tolerances in SURVEY.md 8d are stated in)."""
+    d = np.abs(np.asarray(x, np.float64) - np.asarray(y, np.float64)).max() if np.size(x) else 0.0
+    s = np.abs(np.asarray(y, np.float64)).max() if np.size(y) else 1.0
+    return d / max(s, 1e-300)
+
+
+def frac_rows_within(x, y, tol):
+    """fraction of rows whose max abs difference is <= tol * max|y|"""
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64)
+    s = np.abs(y).max()
+    d = np.abs(x - y).reshape(x.shape[0], -1).max(axis=1)
+    return float((d <= tol * s).mean())
+
+
+def rows_match(x, y, tol, outlier_frac=0.001):
+    """True when all but `outlier_frac` of the rows (at least one row is always allowed) agree to
+    tol * max|y|.  Outliers exist because the CG exits on absolute ||r||^2 thresholds (1e-12 / 1e-8): a row
+    sitting on a threshold can legitimately take one step more or fewer under a different summation order."""
+    x = np.asarray(x, np.float64).reshape(np.shape(x)[0], -1)
+    y = np.asarray(y, np.float64).reshape(np.shape(y)[0], -1)
+    s = max(np.abs(y).max(), 1e-300)
+    bad = int((np.abs(x - y).max(axis=1) > tol * s).sum())
+    return bad <= max(1, int(np.ceil(outlier_frac * x.shape[0])))

@@ -1,0 +1,144 @@
+"""T2 parity: whole fits through the reference-named entry points (include/cmfrec_b200.h PART 1) against the
+reference build with the same arguments and seed.  Tolerances: fp64 1e-7 relative after several iterations
+(differences in summation order compound through the alternation), fp32 5e-3; the initial state (niter=0)
+must be bit-identical."""
+import numpy as np
+import pytest
+
+from support import fit_explicit, fit_implicit, ref, rel_err, rows_match, synth_coo
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float64): 1e-7, np.dtype(np.float32): 5e-3}
+
+
+def _ref(dt):
+    R = ref(dt)
+    if R is None:
+        pytest.fail("oracle/_ref is not built")
+    return R
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_initial_state_bit_exact(gpu_libs, dtype):
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    m, n, k = 3000, 1500, 20
+    ixA, ixB, X = synth_coo(m, n, 40000, dt, seed=3)
+    a = fit_explicit(L, dt, ixA, ixB, X, m, n, k, niter=0, nthreads=4)
+    b = fit_explicit(R, dt, ixA, ixB, X, m, n, k, niter=0, nthreads=4)
+    assert a["rc"] == 0 and b["rc"] == 0
+    for key in ("A", "B", "biasA", "biasB"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["glob_mean"] == b["glob_mean"]
+    ixA, ixB, X = synth_coo(m, n, 40000, dt, seed=4, kind="counts")
+    a = fit_implicit(L, dt, ixA, ixB, X, m, n, k, niter=0)
+    b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, niter=0)
+    assert np.array_equal(a["A"], b["A"]) and np.array_equal(a["B"], b["B"])
+
+
+CASES_EXPLICIT = [
+    dict(),                                                             # default: biases, centre, CG
+    dict(finalize_chol=True),                                           # last iteration exact (CMF default)
+    dict(use_cg=False),                                                 # Cholesky throughout
+    dict(scale_lam=True, lam=0.05),                                     # benchmark hyper-parameters
+    dict(user_bias=False, item_bias=False, center=False),
+    dict(user_bias=True, item_bias=False),
+    dict(user_bias=False, item_bias=True),
+    dict(w_main=2.5, finalize_chol=True),
+    dict(lam_unique=[0.3, 0.2, 0.07, 0.09, 1.0, 1.0], scale_lam=True),
+    dict(k_main=3),
+    dict(max_cg_steps=5, niter=2),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", range(len(CASES_EXPLICIT)))
+def test_explicit_fit_matches_reference(gpu_libs, dtype, case):
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    kw = dict(lam=1.0, niter=3, nthreads=4)
+    kw.update(CASES_EXPLICIT[case])
+    m, n, k = 1200, 700, 16
+    ixA, ixB, X = synth_coo(m, n, 30000, dt, seed=10 + case)
+    a = fit_explicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+    b = fit_explicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+    assert a["rc"] == 0 and b["rc"] == 0
+    assert a["glob_mean"] == b["glob_mean"]
+    tol = TOL[dt]
+    assert rows_match(a["A"], b["A"], tol), rel_err(a["A"], b["A"])
+    assert rows_match(a["B"], b["B"], tol), rel_err(a["B"], b["B"])
+    s = max(np.abs(b["A"]).max(), 1e-30)
+    if kw.get("user_bias", True):
+        assert rows_match(a["biasA"][:, None], b["biasA"][:, None], tol * max(1.0, s / np.abs(b["biasA"]).max()))
+    if kw.get("item_bias", True):
+        assert rows_match(a["biasB"][:, None], b["biasB"][:, None], tol * max(1.0, s / np.abs(b["biasB"]).max()))
+
+
+CASES_IMPLICIT = [
+    dict(),
+    dict(alpha=40.0, lam=1.0),
+    dict(use_cg=False),
+    dict(finalize_chol=True),
+    dict(apply_log_transf=True, alpha=2.0),
+    dict(adjust_weight=True, lam=1e-3),
+    dict(w_main=3.0),
+    dict(k_main=2),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", range(len(CASES_IMPLICIT)))
+def test_implicit_fit_matches_reference(gpu_libs, dtype, case):
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    kw = dict(niter=3, nthreads=4)
+    kw.update(CASES_IMPLICIT[case])
+    m, n, k = 20000, 9000, 16          # > 2^18 factor entries, so the uniform initialiser is taken (Q7)
+    ixA, ixB, X = synth_coo(m, n, 150000, dt, seed=30 + case, kind="counts")
+    a = fit_implicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+    b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+    assert a["rc"] == 0 and b["rc"] == 0
+    assert a["w_main_multiplier"] == b["w_main_multiplier"]
+    tol = TOL[dt]
+    assert rows_match(a["A"], b["A"], tol), rel_err(a["A"], b["A"])
+    assert rows_match(a["B"], b["B"], tol), rel_err(a["B"], b["B"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_precomputed_outputs(gpu_libs, dtype):
+    """precompute_for_predictions: B_plus_bias, BtB (upper triangle), TransBtBinvBt (src/collective.c:8935-9075)"""
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    m, n, k = 900, 500, 12
+    ixA, ixB, X = synth_coo(m, n, 20000, dt, seed=77)
+    kw = dict(lam=0.8, niter=2, precompute=True, finalize_chol=True)
+    a = fit_explicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+    b = fit_explicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+    tol = TOL[dt] * 10
+    assert rel_err(a["B_plus_bias"], b["B_plus_bias"]) <= tol
+    iu = np.triu_indices(k + 1)
+    assert rel_err(a["BtB"][iu], b["BtB"][iu]) <= tol
+    assert rel_err(a["TransBtBinvBt"], b["TransBtBinvBt"]) <= tol
+    ixA, ixB, X = synth_coo(m, n, 20000, dt, seed=78, kind="counts")
+    a = fit_implicit(L, dt, ixA, ixB, X, m, n, k, niter=2, precompute=True)
+    b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, niter=2, precompute=True)
+    assert rel_err(a["BtB"][np.triu_indices(k)], b["BtB"][np.triu_indices(k)]) <= tol
+
+
+def test_unsupported_arguments_are_refused(gpu_libs):
+    """No silent fallback: what the GPU path does not cover returns code 2."""
+    dt = np.dtype(np.float64)
+    L = gpu_libs[dt]
+    m, n, k = 50, 40, 4
+    ixA, ixB, X = synth_coo(m, n, 300, dt, seed=1)
+    from support import ptr
+    A = np.zeros((m, k)); B = np.zeros((n, k)); g = np.zeros(1)
+    w = np.ones(X.size)
+    rc = L.fit_collective_explicit_als(
+        None, None, ptr(A), ptr(B), None, None, None, None, False, True, 1, ptr(g), None, None, m, n, k,
+        ptr(ixA), ptr(ixB), ptr(X), X.size, None, ptr(w), False, False, True, 1.0, None, 0.0, None, False, False, False,
+        None, None, None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False, False,
+        0, 0, 0, 1.0, 1.0, 1.0, 1.0, 2, 1, False, False, True, 3, False, False, False, 100, False, False, False, True,
+        None, None, None, None, None, None, None, None, None)
+    assert rc == 2

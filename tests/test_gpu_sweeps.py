@@ -1,0 +1,146 @@
+"""T1 parity: one half-sweep on the GPU (through the C ABI, include/cmfrec_b200.h PART 2) against the
+reference's optimizeA / optimizeA_implicit (oracle/_ref) from identical inputs.
+
+Tolerances: fp64 max|d| <= 1e-9 * max|A| on >= 99.9 % of rows, fp32 <= 2e-4 * max|A|;
+rows that sit on one of the CG's absolute ||r||^2 thresholds may take a different number of steps.
+"""
+import numpy as np
+import pytest
+
+from support import (AlsSession, csr_csc, ref, ref_optimizeA, ref_optimizeA_implicit, rel_err, rows_match,
+                     synth_coo)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float64): 1e-9, np.dtype(np.float32): 2e-4}
+
+
+def _need_ref(dt):
+    R = ref(dt)
+    if R is None:
+        pytest.fail("oracle/_ref is not built (run `make -C oracle` where /root/reference exists)")
+    return R
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("k", [3, 16, 40, 64, 100, 128, 200])
+@pytest.mark.parametrize("solver", ["cg", "chol"])
+def test_implicit_half_sweeps(gpu_libs, dtype, k, solver):
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _need_ref(dt)
+    m, n = 700, 450
+    ixA, ixB, X = synth_coo(m, n, 9000, dt, seed=k, kind="counts")
+    csr = csr_csc(L, dt, ixA, ixB, X, m, n)
+    rng = np.random.default_rng(k)
+    A0 = (rng.random((m, k)) * 0.1).astype(dt)
+    B0 = (rng.random((n, k)) * 0.1).astype(dt)
+    lam = 3.0
+    use_cg = solver == "cg"
+    with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=True, lam_A=lam, lam_B=lam) as s:
+        s.set_factors(A0, None, B0, None)
+        s.half_sweep(0, 0, 0 if use_cg else 1)          # B from A
+        _, B1 = s.get_factors()
+        s.half_sweep(1, 0, 0 if use_cg else 1)          # A from the new B
+        A1, _ = s.get_factors()
+    Bref = B0.copy()
+    ref_optimizeA_implicit(R, dt, Bref, A0.copy(), csr[3], csr[4], csr[5], lam=lam, use_cg=use_cg, max_cg_steps=3)
+    Aref = A0.copy()
+    ref_optimizeA_implicit(R, dt, Aref, Bref.copy(), csr[0], csr[1], csr[2], lam=lam, use_cg=use_cg, max_cg_steps=3)
+    assert rows_match(B1, Bref, TOL[dt]), rel_err(B1, Bref)
+    # the A sweep starts from the GPU's B, which already differs from the reference's within tolerance
+    assert rows_match(A1, Aref, 10 * TOL[dt]), rel_err(A1, Aref)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("k", [3, 16, 40, 64, 128])
+@pytest.mark.parametrize("solver", ["cg", "chol"])
+@pytest.mark.parametrize("biases", [(True, True), (False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("scale_lam", [False, True])
+def test_explicit_half_sweeps(gpu_libs, dtype, k, solver, biases, scale_lam):
+    """The reference is driven exactly like its fit loop does (src/collective.c:8538-8882): bias as last
+    column, opposing last column forced to 1, X re-centred by the opposing bias."""
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _need_ref(dt)
+    user_bias, item_bias = biases
+    m, n = 600, 380
+    ixA, ixB, X = synth_coo(m, n, 8000, dt, seed=100 + k)
+    X = (X - X.mean()).astype(dt)
+    csr = csr_csc(L, dt, ixA, ixB, X, m, n)
+    rng = np.random.default_rng(k)
+    A0 = (rng.normal(size=(m, k)) * 0.1).astype(dt)
+    B0 = (rng.normal(size=(n, k)) * 0.1).astype(dt)
+    bA0 = (rng.normal(size=m) * 0.3).astype(dt) if user_bias else None
+    bB0 = (rng.normal(size=n) * 0.3).astype(dt) if item_bias else None
+    lam, lam_bias = (0.05, 0.11) if scale_lam else (1.5, 2.5)
+    use_cg = solver == "cg"
+    sv = 0 if use_cg else 1
+    it = 1  # an iteration index > 0: with both biases the solved bias coordinate restarts from 1.0
+    with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=False, user_bias=user_bias, item_bias=item_bias,
+                    lam_A=lam, lam_B=lam, lam_biasA=lam_bias, lam_biasB=lam_bias, scale_lam=scale_lam) as s:
+        s.set_factors(A0, bA0, B0, bB0)
+        s.half_sweep(0, it, sv)
+        _, _, B1, bB1 = s.get_factors(with_bias=True)
+        s.half_sweep(1, it, sv)
+        A1, bA1, _, _ = s.get_factors(with_bias=True)
+
+    has_bias = user_bias or item_bias
+    kd = k + int(has_bias)
+
+    def with_col(M, col):
+        out = np.zeros((M.shape[0], kd), dt)
+        out[:, :k] = M
+        if has_bias:
+            out[:, k] = col
+        return out
+
+    both = user_bias and item_bias
+    # ---- B sweep as the reference sets it up
+    A_b = with_col(A0, 1.0 if item_bias else (bA0 if user_bias else 0.0))
+    B_b = with_col(B0, (1.0 if both else bB0) if item_bias else 1.0)
+    Xcsc = csr[5] - (bA0[csr[4]] if user_bias else 0)
+    kB = k + int(item_bias)
+    Bsol = np.ascontiguousarray(B_b[:, :kB])
+    ref_optimizeA(R, dt, Bsol, np.ascontiguousarray(A_b[:, :kB]), csr[3], csr[4], Xcsc.astype(dt), lam=lam,
+                  lam_last=lam_bias if item_bias else lam, scale_lam=scale_lam, use_cg=use_cg, max_cg_steps=3)
+    Bref = Bsol[:, :k]
+    bBref = Bsol[:, k] if item_bias else None
+    tol = TOL[dt]
+    assert rows_match(B1, Bref, tol), rel_err(B1, Bref)
+    if item_bias:
+        assert rows_match(bB1[:, None], bBref[:, None], tol * max(1.0, np.abs(Bref).max() / np.abs(bBref).max()))
+
+    # ---- A sweep, starting from the reference's own B
+    B_b2 = with_col(Bref, 1.0 if user_bias else (bBref if item_bias else 0.0))
+    A_b2 = with_col(A0, (1.0 if both else bA0) if user_bias else 1.0)
+    Xcsr = csr[2] - (bBref[csr[1]] if item_bias else 0)
+    kA = k + int(user_bias)
+    Asol = np.ascontiguousarray(A_b2[:, :kA])
+    ref_optimizeA(R, dt, Asol, np.ascontiguousarray(B_b2[:, :kA]), csr[0], csr[1], Xcsr.astype(dt), lam=lam,
+                  lam_last=lam_bias if user_bias else lam, scale_lam=scale_lam, use_cg=use_cg, max_cg_steps=3)
+    assert rows_match(A1, Asol[:, :k], 10 * tol), rel_err(A1, Asol[:, :k])
+    if user_bias:
+        assert rows_match(bA1[:, None], Asol[:, k:kA], 10 * tol * max(1.0, np.abs(Asol[:, :k]).max() / np.abs(Asol[:, k]).max()))
+
+
+def test_long_rows_take_block_path(gpu_libs):
+    """Rows longer than the block-per-row threshold (default 2048 entries) must give the same answer."""
+    dt = np.dtype(np.float64)
+    L, R = gpu_libs[dt], _need_ref(dt)
+    m, n, k = 40, 6000, 32
+    rng = np.random.default_rng(5)
+    rows, cols = [], []
+    for r in range(m):
+        deg = 5000 if r < 3 else 50
+        c = np.sort(rng.choice(n, deg, replace=False))
+        rows.append(np.full(deg, r)); cols.append(c)
+    ixA = np.concatenate(rows).astype(np.int32); ixB = np.concatenate(cols).astype(np.int32)
+    X = np.ceil(rng.lognormal(1, 1, ixA.size)).astype(dt)
+    csr = csr_csc(L, dt, ixA, ixB, X, m, n)
+    A0 = (rng.random((m, k)) * 0.1).astype(dt); B0 = (rng.random((n, k)) * 0.1).astype(dt)
+    with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=True, lam_A=2.0, lam_B=2.0) as s:
+        s.set_factors(A0, None, B0, None)
+        s.half_sweep(1, 0, 0)
+        A1, _ = s.get_factors()
+    Aref = A0.copy()
+    ref_optimizeA_implicit(R, dt, Aref, B0.copy(), csr[0], csr[1], csr[2], lam=2.0, use_cg=True, max_cg_steps=3)
+    assert rel_err(A1, Aref) <= 1e-9
