@@ -19,15 +19,17 @@ namespace cmfb200 {
 
 namespace {
 
-constexpr int NT = 256;      // threads per block
 constexpr int NB = 16;       // stored entries staged per round
 
-template <typename T, int TPT, bool IMPLICIT>
-__global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, int kd, int kdp, int ntile_rows)
+// NT threads per block, TPT register tiles per thread; MG: the kd x kd matrix does not fit in shared memory
+// and lives in a per-block slice of a global workspace instead (it stays in L2).
+template <typename T, int NT, int TPT, bool IMPLICIT, bool MG>
+__global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, int kd, int kdp, int ntile_rows,
+                                                        T *__restrict__ workspace)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *M = reinterpret_cast<T *>(smem_raw);          // [kd][kdp]   (kdp = padded row length)
-    T *gs = M + (size_t)kd * kdp;                    // [NB][kdp]   staged opposing rows
+    T *M = MG ? workspace + (size_t)blockIdx.x * kd * kdp : reinterpret_cast<T *>(smem_raw);   // [kd][kdp]
+    T *gs = MG ? reinterpret_cast<T *>(smem_raw) : M + (size_t)kd * kdp;   // [NB][kdp] staged opposing rows
     T *wgt = gs + NB * kdp;                          // [NB]        matrix weight of each staged entry
     T *xr = wgt + NB;                                // [NB]        right-hand-side weight
     T *rhs = xr + NB;                                // [kdp]
@@ -198,17 +200,36 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
     }
 }
 
-template <typename T> size_t chol_smem_bytes(int kd, int kdp, int ntile_rows)
+template <typename T> size_t chol_smem_bytes(int kd, int kdp, int ntile_rows, bool matrix_in_smem)
 {
     const size_t ntiles = (size_t)ntile_rows * (ntile_rows + 1) / 2;
-    return ((size_t)kd * kdp + (size_t)NB * kdp + 2 * NB + 3 * (size_t)kdp) * sizeof(T) + ntiles * 2 * sizeof(unsigned short) + 16;
+    return ((matrix_in_smem ? (size_t)kd * kdp : 0) + (size_t)NB * kdp + 2 * NB + 3 * (size_t)kdp) * sizeof(T) +
+           ntiles * 2 * sizeof(unsigned short) + 16;
 }
 
-template <typename T, int TPT, bool IMPLICIT>
+// per-device scratch for the MG variant, grown on demand and kept for the life of the process
+template <typename T> T *chol_workspace(size_t elems)
+{
+    static T *buf[64] = {nullptr};
+    static size_t cap[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (cap[dev] < elems) {
+        if (buf[dev]) cudaFree(buf[dev]);
+        buf[dev] = nullptr;
+        cap[dev] = 0;
+        if (cudaMalloc((void **)&buf[dev], elems * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cap[dev] = elems;
+    }
+    return buf[dev];
+}
+
+template <typename T, int NT, int TPT, bool IMPLICIT, bool MG>
 int launch_tpt(const CgSweepParams &p, int kd, int kdp, int ntile_rows, cudaStream_t stream)
 {
-    const size_t smem = chol_smem_bytes<T>(kd, kdp, ntile_rows);
-    auto kern = chol_sweep_kernel<T, TPT, IMPLICIT>;
+    const size_t smem = chol_smem_bytes<T>(kd, kdp, ntile_rows, !MG);
+    auto kern = chol_sweep_kernel<T, NT, TPT, IMPLICIT, MG>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 2;
@@ -221,7 +242,12 @@ int launch_tpt(const CgSweepParams &p, int kd, int kdp, int ntile_rows, cudaStre
     long long grid = (long long)sms * occ;
     if (grid > p.plan.n_rows) grid = p.plan.n_rows;
     if (grid < 1) return 0;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(p, kd, kdp, ntile_rows);
+    T *ws = nullptr;
+    if (MG) {
+        ws = chol_workspace<T>((size_t)grid * kd * kdp);
+        if (!ws) return 1;
+    }
+    kern<<<(unsigned)grid, NT, smem, stream>>>(p, kd, kdp, ntile_rows, ws);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -233,16 +259,26 @@ template <bool IMPLICIT> int dispatch_chol(const CgSweepParams &p, cudaStream_t 
     int kdp = ntile_rows * 4;
     if ((kdp & 31) == 0) kdp += 4;   // keep consecutive rows of M off the same banks
     const int ntiles = ntile_rows * (ntile_rows + 1) / 2;
-    const int tpt = (ntiles + NT - 1) / NT;
-    if (chol_smem_bytes<T>(kd, kdp, ntile_rows) > 227 * 1024) return 2;
-    if (tpt <= 1) return launch_tpt<T, 1, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
-    if (tpt <= 2) return launch_tpt<T, 2, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
-    if (tpt <= 3) return launch_tpt<T, 3, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
-    if (tpt <= 4) return launch_tpt<T, 4, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+    const bool in_smem = chol_smem_bytes<T>(kd, kdp, ntile_rows, true) <= 220 * 1024;
+    const int tpt256 = (ntiles + 255) / 256;
+    const int tpt512 = (ntiles + 511) / 512;
+    if (in_smem) {
+        if (tpt256 <= 1) return launch_tpt<T, 256, 1, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt256 <= 2) return launch_tpt<T, 256, 2, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt256 <= 3) return launch_tpt<T, 256, 3, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt512 <= 2) return launch_tpt<T, 512, 2, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt512 <= 3) return launch_tpt<T, 512, 3, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
 #ifdef USE_FLOAT
-    if (tpt <= 7) return launch_tpt<T, 7, IMPLICIT>(p, kd, kdp, ntile_rows, stream);
+        if (tpt512 <= 5) return launch_tpt<T, 512, 5, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
 #endif
-    return 2;
+        return 2;
+    }
+    if (tpt512 <= 2) return launch_tpt<T, 512, 2, IMPLICIT, true>(p, kd, kdp, ntile_rows, stream);
+    if (tpt512 <= 3) return launch_tpt<T, 512, 3, IMPLICIT, true>(p, kd, kdp, ntile_rows, stream);
+#ifdef USE_FLOAT
+    if (tpt512 <= 5) return launch_tpt<T, 512, 5, IMPLICIT, true>(p, kd, kdp, ntile_rows, stream);
+#endif
+    return 2;   // fp32: k up to ~280, fp64: k up to ~215
 }
 
 }  // namespace

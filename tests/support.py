@@ -200,3 +200,22 @@ def rows_match(x, y, tol, outlier_frac=0.001):
     s = max(np.abs(y).max(), 1e-300)
     bad = int((np.abs(x - y).max(axis=1) > tol * s).sum())
     return bad <= max(1, int(np.ceil(outlier_frac * x.shape[0])))
+
+
+def implicit_objective(ixA, ixB, X, A, B, lam, alpha=1.0):
+    """WRMF loss the implicit fit minimises, in float64: sum_all (p - a.b)^2 + sum_nz x (1 - a.b)^2-ish form
+    written through the Gram trick: sum_all (a.b)^2 = <A^T A, B^T B>."""
+    A = np.asarray(A, np.float64); B = np.asarray(B, np.float64); x = np.asarray(X, np.float64) * alpha
+    pred = np.einsum("ij,ij->i", A[ixA], B[ixB])
+    all_sq = np.sum((A.T @ A) * (B.T @ B))
+    loss = all_sq + np.sum((x + 1.0) * (1.0 - pred) ** 2 - pred ** 2)
+    return loss + lam * (np.sum(A * A) + np.sum(B * B))
+
+
+def explicit_objective(ixA, ixB, X, out, lam):
+    """squared error on the stored entries + L2 penalty, float64"""
+    A = np.asarray(out["A"], np.float64); B = np.asarray(out["B"], np.float64)
+    pred = np.einsum("ij,ij->i", A[ixA], B[ixB]) + float(out["glob_mean"])
+    pred = pred + np.asarray(out["biasA"], np.float64)[ixA] + np.asarray(out["biasB"], np.float64)[ixB]
+    err = np.asarray(X, np.float64) - pred
+    return np.sum(err ** 2) + lam * (np.sum(A * A) + np.sum(B * B))

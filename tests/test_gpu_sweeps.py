@@ -12,7 +12,10 @@ from support import (AlsSession, csr_csc, ref, ref_optimizeA, ref_optimizeA_impl
 
 pytestmark = pytest.mark.gpu
 
-TOL = {np.dtype(np.float64): 1e-9, np.dtype(np.float32): 2e-4}
+# fp32: the reference's own float result sits 3-5e-4 (relative to max|A|) away from exact arithmetic on these
+# problems (bias coordinate restarted from 1.0, condition number ~1e2), so 1e-3 is the meaningful bound;
+# test_fp32_accuracy_is_the_references below additionally pins the GPU error to the reference's error.
+TOL = {np.dtype(np.float64): 1e-9, np.dtype(np.float32): 1e-3}
 
 
 def _need_ref(dt):
@@ -48,7 +51,7 @@ def test_implicit_half_sweeps(gpu_libs, dtype, k, solver):
     ref_optimizeA_implicit(R, dt, Aref, Bref.copy(), csr[0], csr[1], csr[2], lam=lam, use_cg=use_cg, max_cg_steps=3)
     assert rows_match(B1, Bref, TOL[dt]), rel_err(B1, Bref)
     # the A sweep starts from the GPU's B, which already differs from the reference's within tolerance
-    assert rows_match(A1, Aref, 10 * TOL[dt]), rel_err(A1, Aref)
+    assert rows_match(A1, Aref, 5 * TOL[dt]), rel_err(A1, Aref)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -117,9 +120,9 @@ def test_explicit_half_sweeps(gpu_libs, dtype, k, solver, biases, scale_lam):
     Asol = np.ascontiguousarray(A_b2[:, :kA])
     ref_optimizeA(R, dt, Asol, np.ascontiguousarray(B_b2[:, :kA]), csr[0], csr[1], Xcsr.astype(dt), lam=lam,
                   lam_last=lam_bias if user_bias else lam, scale_lam=scale_lam, use_cg=use_cg, max_cg_steps=3)
-    assert rows_match(A1, Asol[:, :k], 10 * tol), rel_err(A1, Asol[:, :k])
+    assert rows_match(A1, Asol[:, :k], 5 * tol), rel_err(A1, Asol[:, :k])
     if user_bias:
-        assert rows_match(bA1[:, None], Asol[:, k:kA], 10 * tol * max(1.0, np.abs(Asol[:, :k]).max() / np.abs(Asol[:, k]).max()))
+        assert rows_match(bA1[:, None], Asol[:, k:kA], 5 * tol * max(1.0, np.abs(Asol[:, :k]).max() / np.abs(Asol[:, k]).max()))
 
 
 def test_long_rows_take_block_path(gpu_libs):
@@ -144,3 +147,51 @@ def test_long_rows_take_block_path(gpu_libs):
     Aref = A0.copy()
     ref_optimizeA_implicit(R, dt, Aref, B0.copy(), csr[0], csr[1], csr[2], lam=2.0, use_cg=True, max_cg_steps=3)
     assert rel_err(A1, Aref) <= 1e-9
+
+
+@pytest.mark.parametrize("k", [3, 16, 64, 128])
+@pytest.mark.parametrize("implicit", [False, True])
+def test_fp32_accuracy_is_the_references(gpu_libs, k, implicit):
+    """float32 half-sweep: error against exact (float64) arithmetic on the same inputs must not exceed 3x the
+    reference's own float32 error -- i.e. the GPU is as close to the true CG iterate as the reference is."""
+    from oracle import restatement as O
+    dt = np.dtype(np.float32)
+    L, R = gpu_libs[dt], _need_ref(dt)
+    m, n = 600, 380
+    ixA, ixB, X = synth_coo(m, n, 8000, dt, seed=200 + k, kind="counts" if implicit else "ratings")
+    if not implicit:
+        X = (X - X.mean()).astype(dt)
+    csr = csr_csc(L, dt, ixA, ixB, X, m, n)
+    rng = np.random.default_rng(k)
+    A0 = (rng.normal(size=(m, k)) * 0.1).astype(dt)
+    B0 = (rng.normal(size=(n, k)) * 0.1).astype(dt)
+    if implicit:
+        A0, B0 = np.abs(A0), np.abs(B0)
+        with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=True, lam_A=3.0, lam_B=3.0) as s:
+            s.set_factors(A0, None, B0, None)
+            s.half_sweep(0, 0, 0)
+            _, G = s.get_factors()
+        Rr = B0.copy(); ref_optimizeA_implicit(R, dt, Rr, A0.copy(), csr[3], csr[4], csr[5], lam=3.0, use_cg=True, max_cg_steps=3)
+        T = B0.astype(np.float64)
+        O.optimizeA_implicit(np.float64, T, A0.astype(np.float64), csr[3], csr[4], csr[5].astype(np.float64), lam=3.0,
+                             use_cg=True, max_cg_steps=3)
+    else:
+        bA0 = (rng.normal(size=m) * 0.3).astype(dt); bB0 = (rng.normal(size=n) * 0.3).astype(dt)
+        with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=False, user_bias=True, item_bias=True, lam_A=1.5,
+                        lam_B=1.5, lam_biasA=2.5, lam_biasB=2.5) as s:
+            s.set_factors(A0, bA0, B0, bB0)
+            s.half_sweep(0, 1, 0)
+            _, _, Bg, bBg = s.get_factors(with_bias=True)
+        G = np.concatenate([Bg, bBg[:, None]], 1)
+        one = np.ones((1,), dt)
+        A_b = np.concatenate([A0, np.ones((m, 1), dt)], 1); B_b = np.concatenate([B0, np.ones((n, 1), dt)], 1)
+        Xcsc = (csr[5] - bA0[csr[4]]).astype(dt)
+        Rr = B_b.copy(); ref_optimizeA(R, dt, Rr, A_b.copy(), csr[3], csr[4], Xcsc, lam=1.5, lam_last=2.5, scale_lam=False,
+                                       use_cg=True, max_cg_steps=3)
+        T = B_b.astype(np.float64)
+        O.optimizeA(np.float64, T, A_b.astype(np.float64), csr[3], csr[4], Xcsc.astype(np.float64), lam=1.5, lam_last=2.5,
+                    scale_lam=False, use_cg=True, max_cg_steps=3)
+    # 99.5th percentile of the row errors: robust to the occasional row sitting on a CG exit threshold
+    e_gpu = np.quantile(np.abs(G - T).max(axis=1), 0.995)
+    e_ref = np.quantile(np.abs(Rr - T).max(axis=1), 0.995)
+    assert e_gpu <= 3 * e_ref + 1e-6, (e_gpu, e_ref)
