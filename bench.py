@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the ALS hot path (BASELINE.json metric: rows solved / s and s per ALS iteration at k=64 on an
+ML10M-shaped CSR).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one full ALS iteration (B half-sweep + A half-sweep) over the whole synthetic matrix.
+  value        rows solved per second, whole job, inputs resident in HBM (CUDA-event time of the K steps,
+               max over ranks, L2 flushed between steps)
+  e2e          the same metric through the host-pointer C ABI (fit_collective_*_als with numpy buffers):
+               centring, COO->CSR/CSC, bias / factor initialisation, H2D, K iterations, D2H all inside the timed region
+  roofline     achieved algorithmic GB/s of the row-solve kernel (CUDA events around every launch of it inside the
+               timed region) against the measured HBM copy bandwidth
+  cpu_baseline the reference's own OpenMP+BLAS implementation (oracle/_ref, built from /root/reference) on the box's
+               host cores, same workload
+`--impl reference` times only that CPU implementation and prints the line with "impl": "reference".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: shape, implicit, k, dtype, solver, extra
+    "ml10m_explicit_cg_k64_f32": dict(shape="ml10m", implicit=False, k=64, dtype="f32", use_cg=True),
+    "lastfm_implicit_cg_k64_f32": dict(shape="lastfm", implicit=True, k=64, dtype="f32", use_cg=True),
+    "ml10m_explicit_chol_k64_f32": dict(shape="ml10m", implicit=False, k=64, dtype="f32", use_cg=False),
+    "ml10m_explicit_cg_k128_f32": dict(shape="ml10m", implicit=False, k=128, dtype="f32", use_cg=True),
+    "lastfm_implicit_cg_k128_f32": dict(shape="lastfm", implicit=True, k=128, dtype="f32", use_cg=True),
+    "lastfm_implicit_cg_k256_f32": dict(shape="lastfm", implicit=True, k=256, dtype="f32", use_cg=True),
+    "cfg1_explicit_cg_k16_f64": dict(shape="cfg1", implicit=False, k=16, dtype="f64", use_cg=True),
+}
+HYPER = dict(explicit=dict(lam=0.05, scale_lam=True, user_bias=True, item_bias=True, center=True, max_cg_steps=3),
+             implicit=dict(lam=5.0, alpha=1.0, max_cg_steps=3))
+
+
+def load_data(w):
+    from cmfrec_b200 import synth
+    dt = np.dtype(np.float32 if w["dtype"] == "f32" else np.float64)
+    cache = os.path.join("/tmp", "cmfb200_%s_%s.npz" % (w["shape"], w["dtype"]))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["a"], z["b"], z["x"], int(z["m"]), int(z["n"]), dt
+    a, b, x, m, n = synth.make(w["shape"], dt)
+    try:
+        np.savez(cache + ".tmp.npz", a=a, b=b, x=x, m=m, n=n)
+        os.replace(cache + ".tmp.npz", cache)
+    except OSError:
+        pass
+    return a, b, x, m, n, dt
+
+
+def algorithmic_bytes(w, m, n, nnz, dt):
+    """every stored entry gathers its opposing row once per half-sweep, plus CSR index+value,
+    plus indptr and read+write of the solved row; implicit adds one pass over the opposing factor for the Gram."""
+    wd = dt.itemsize
+    k1 = w["k"] + (0 if w["implicit"] else 1)
+    half = lambda rows, opp: nnz * (k1 * wd + 4 + wd) + rows * (8 + 2 * k1 * wd) + (opp * w["k"] * wd if w["implicit"] else 0)
+    return half(n, m), half(m, n)       # (B sweep, A sweep)
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def time_reference(w, data, steps, warmup, nthreads):
+    """The reference's own CPU implementation of the same fit: sec / iteration = (t(K iters) - t(0 iters)) / K."""
+    import refload
+    from support import fit_explicit, fit_implicit
+    a, b, x, m, n, dt = data
+    R = refload.ref(dt)
+    kind = "reference"
+    if R is None:
+        raise RuntimeError("oracle/_ref missing: build it where /root/reference exists (make -C oracle ref)")
+    if w["implicit"]:
+        h = HYPER["implicit"]
+        run = lambda it: fit_implicit(R, dt, a, b, x, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=it,
+                                      use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthreads)
+    else:
+        h = HYPER["explicit"]
+        run = lambda it: fit_explicit(R, dt, a, b, x, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"], niter=it,
+                                      use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthreads)
+    run(max(1, min(warmup, 1)))
+    t0 = time.perf_counter(); run(0); t_prep = time.perf_counter() - t0
+    t0 = time.perf_counter(); out = run(steps); t_full = time.perf_counter() - t0
+    assert out["rc"] == 0
+    sec_iter = max(t_full - t_prep, 1e-9) / steps
+    return dict(sec_iter=sec_iter, rows_per_s=(m + n) / sec_iter, kind=kind, prep_s=t_prep,
+                sample="full workload, %d ALS iterations (fit time minus a 0-iteration fit), nthreads=%d" % (steps, nthreads))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml10m_explicit_cg_k64_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncpu = os.cpu_count() or 1
+    config = dict(workload=args.workload, shape=w["shape"], k=w["k"], solver="cg" if w["use_cg"] else "cholesky",
+                  feedback="implicit" if w["implicit"] else "explicit",
+                  hyper=HYPER["implicit" if w["implicit"] else "explicit"],
+                  l2="flushed between steps (256 MiB memset); CSR+CSC streamed per step exceed L2",
+                  parallelism="rows of A and of B dealt over %d GPU(s); all-gather after each half-sweep" % world)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        data = load_data(w)
+        r = time_reference(w, data, args.steps, args.warmup, ncpu)
+        m, n = data[3], data[4]
+        config.update(m=m, n=n, nnz=int(data[2].size))
+        line = dict(impl="reference", metric="rows_solved_per_sec", value=r["rows_per_s"], unit="rows/s",
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=r["sec_iter"] * 1e3,
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype=w["dtype"], data="synthetic",
+                    config=config,
+                    cpu_baseline=dict(value=r["rows_per_s"], unit="rows/s", cores=ncpu, kind=r["kind"], sample=r["sample"]),
+                    e2e=dict(value=r["rows_per_s"], unit="rows/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, sec_per_iter=r["sec_iter"])
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cmfrec_b200 import _lib
+    from support import csr_csc, fit_explicit, fit_implicit
+    from refload import ptr
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    a, b, x, m, n, dt = data = load_data(w)
+    nnz = int(x.size)
+    config.update(m=m, n=n, nnz=nnz)
+    L = _lib.load(dt)
+    if L.cmfb200_device_count() < 1:
+        raise RuntimeError("no CUDA device: cmfrec_b200 has no CPU path")
+
+    # ---- prepare exactly what the fit entry point prepares
+    if w["implicit"]:
+        h = HYPER["implicit"]
+        xs = (x * dt.type(h["alpha"])).astype(dt)
+        csr = csr_csc(L, dt, a, b, xs, m, n)
+        A0 = np.zeros((m, w["k"]), dt); B0 = np.zeros((n, w["k"]), dt)
+        L.cmfb200_random_init(ptr(A0), A0.size, None, 0, 1, False)
+        bA = bB = None
+        lamA = lamB = lbA = lbB = h["lam"]
+    else:
+        h = HYPER["explicit"]
+        mu = L.cmfb200_global_mean(ptr(x), nnz, ncpu)
+        xc = (x - dt.type(mu)).astype(dt)
+        csr = csr_csc(L, dt, a, b, xc, m, n)
+        bA = np.zeros(m, dt); bB = np.zeros(n, dt)
+        L.cmfb200_init_biases_twosided(m, n, *[ptr(t) for t in csr], h["lam"], h["lam"], h["scale_lam"], False, ptr(bA), ptr(bB), ncpu)
+        A0 = np.zeros((m, w["k"]), dt); B0 = np.zeros((n, w["k"]), dt)
+        L.cmfb200_random_init(ptr(A0), A0.size, None, 0, 1, True)
+        lamA = lamB = lbA = lbB = h["lam"]
+
+    stream = torch.cuda.current_stream().cuda_stream
+    opt = L.AlsOptions()
+    opt.implicit = int(w["implicit"])
+    opt.m, opt.n, opt.k = m, n, w["k"]
+    opt.user_bias = opt.item_bias = int(not w["implicit"])
+    opt.lam_A, opt.lam_B, opt.lam_biasA, opt.lam_biasB = lamA, lamB, lbA, lbB
+    opt.scale_lam = int((not w["implicit"]) and h["scale_lam"])
+    opt.max_cg_steps = h["max_cg_steps"]
+    opt.rank, opt.world = rank, world
+    idbuf = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            assert L.cmfb200_nccl_unique_id(raw) == 0
+            idt = torch.tensor(list(raw), dtype=torch.uint8)
+        idt = idt.cuda()
+        dist.broadcast(idt, 0)
+        idbuf = (C.c_ubyte * 128)(*idt.cpu().tolist())
+        opt.nccl_id = C.cast(idbuf, C.c_void_p)
+    opt.stream = stream
+    hnd = C.c_void_p()
+    rc = L.cmfb200_als_create(C.byref(hnd), C.byref(opt), *[ptr(t) for t in csr])
+    assert rc == 0, "cmfb200_als_create -> %d" % rc
+    assert L.cmfb200_als_set_factors(hnd, ptr(A0), ptr(bA), ptr(B0), ptr(bB)) == 0
+    use_cg = int(w["use_cg"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ms = C.c_float(0)
+    it = 0
+    for _ in range(max(args.warmup, 3)):
+        assert L.cmfb200_als_timed_iterate(hnd, it, 1, 1 << 30, use_cg, 0, C.byref(ms)) == 0
+        it += 1
+    L.cmfb200_als_set_profile(hnd, 1)
+    launches0 = L.cmfb200_als_launch_count(hnd)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()                                           # evict L2 (not timed)
+        assert L.cmfb200_als_timed_iterate(hnd, it, 1, 1 << 30, use_cg, 0, C.byref(ms)) == 0
+        total_ms += ms.value
+        it += 1
+    barrier()
+    clocks = sampler.stop()
+    launches = L.cmfb200_als_launch_count(hnd) - launches0
+    kt = [C.c_double(0), C.c_double(0)]
+    kc = [C.c_longlong(0), C.c_longlong(0)]
+    for which in (0, 1):
+        L.cmfb200_als_read_profile(hnd, which, C.byref(kt[which]), C.byref(kc[which]))
+    L.cmfb200_als_set_profile(hnd, 0)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = (m + n) / (ms_per_step * 1e-3)
+
+    # roofline of the row-solve kernel (both launches of a step are the same kernel on the two orientations)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    bytes_B, bytes_A = algorithmic_bytes(w, m, n, nnz, dt)
+    kernel_ms = kt[0].value + kt[1].value
+    kernel_launches = kc[0].value + kc[1].value
+    bytes_per_launch = (bytes_B + bytes_A) / 2.0 / world
+    avg_ms = kernel_ms / max(kernel_launches, 1)
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    kernel="cg_sweep_kernel" if w["use_cg"] else "chol_sweep_kernel", avg_launch_ms=avg_ms,
+                    launches_timed=int(kernel_launches), algorithmic_bytes_per_launch=bytes_per_launch,
+                    kernel_share_of_step=kernel_ms / total_ms if total_ms else None, peak_source=peak_src,
+                    B_sweep_ms=kt[0].value / max(kc[0].value, 1), A_sweep_ms=kt[1].value / max(kc[1].value, 1))
+    L.cmfb200_als_destroy(hnd)
+    del flush
+
+    # ---- end to end through the host-pointer C ABI
+    e2e = None
+    if not args.no_e2e:
+        K = args.steps
+        if world == 1:
+            if w["implicit"]:
+                run = lambda nit: fit_implicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=nit,
+                                               use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu)
+            else:
+                run = lambda nit: fit_explicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
+                                               niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu)
+            run(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = run(K)
+            t_e2e = time.perf_counter() - t0
+            assert out["rc"] == 0
+            wd = dt.itemsize
+            ld = ((w["k"] + 1) * wd + 15) // 16 * 16
+            h2d = 2 * (nnz * (4 + wd)) + (m + n + 2) * 8 + (m + n) * ld + (m + n) * 4
+            d2h = (m + n) * ld
+            e2e = dict(value=(m + n) * K / t_e2e, unit="rows/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K,
+                       seconds=t_e2e, iterations=K,
+                       what="one fit_collective_%s_als call, numpy in / numpy out" % ("implicit" if w["implicit"] else "explicit"))
+        else:
+            e2e = dict(value=None, unit="rows/s", h2d_bytes_per_step=None, d2h_bytes_per_step=None,
+                       what="host-pointer entry point is single-GPU in this round")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = time_reference(w, data, 2, 1, ncpu)
+            cpu = dict(value=r["rows_per_s"], unit="rows/s", cores=ncpu, kind=r["kind"], sample=r["sample"],
+                       sec_per_iter=r["sec_iter"])
+        except Exception as e:  # noqa: BLE001
+            cpu = dict(value=None, unit="rows/s", cores=ncpu, kind="reference", sample="unavailable: %s" % e)
+
+    if rank == 0:
+        line = dict(metric="rows_solved_per_sec", value=value, unit="rows/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype=w["dtype"], data="synthetic", config=config, sec_per_iter=ms_per_step * 1e-3,
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,7 @@ static int long_row_threshold()
     static int v = -1;
     if (v < 0) {
         const char *e = std::getenv("CMFB200_LONG_ROW");
-        v = e ? std::atoi(e) : 2048;
+        v = e ? std::atoi(e) : 1024;
         if (v < 64) v = 64;
     }
     return v;
@@ -102,7 +102,30 @@ static int build_side(const size_t *ptr, const int_t *idx, const real_t *val, co
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
-AlsState::~AlsState() { delete link; }
+AlsState::~AlsState()
+{
+    for (auto &v : sweep_events)
+        for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    delete link;
+}
+
+int AlsState::read_profile(int which, double *total_ms, long long *count)
+{
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+    auto &v = sweep_events[which ? 1 : 0];
+    double tot = 0;
+    for (auto &pr : v) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pr.first, pr.second);
+        tot += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = (long long)v.size();
+    v.clear();
+    return 0;
+}
 
 int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
                     const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, cudaStream_t s, const void *nccl_id)
@@ -216,10 +239,20 @@ int AlsState::half_sweep(int which, int iter, int solver)
         p.bias_start_one = both && (solveA || iter > 0);
     }
     int rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profile) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+    }
     if (solver == 0) {
         rc = cfg.implicit ? launch_implicit_cg_sweep(p, stream) : launch_explicit_cg_sweep(p, stream);
     } else {
         rc = cfg.implicit ? launch_implicit_chol_sweep(p, stream) : launch_explicit_chol_sweep(p, stream);
+    }
+    if (profile) {
+        cudaEventRecord(e1, stream);
+        sweep_events[which ? 1 : 0].emplace_back(e0, e1);
     }
     launches += 1;
     return rc;

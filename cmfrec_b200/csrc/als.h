@@ -4,6 +4,7 @@
 // (src/collective.c:8334-8898) and fit_collective_implicit_als (src/collective.c:9827-10040) for models
 // without side information.
 #pragma once
+#include <utility>
 #include <vector>
 #include <cuda_runtime.h>
 #include "cmf_types.h"
@@ -74,6 +75,10 @@ public:
     DevBuf<real_t> gram, gram_ws;
     NcclLink *link = nullptr;
     long long launches = 0;       // kernels launched so far (for bench.py's gpu_launches)
+    // optional per-launch timing of the row-solve kernel (CUDA events on `stream`, resolved on demand)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events[2];   // [which]
+    int read_profile(int which, double *total_ms, long long *count);    // synchronises the stream
 
     ~AlsState();
     // host CSR/CSC in caller numbering (values already centred / scaled as the model requires)

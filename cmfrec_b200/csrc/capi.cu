@@ -191,6 +191,13 @@ int cmfb200_als_timed_iterate(cmfb200_als *s, int first_iter, int n_iters, int n
     return rc;
 }
 
+void cmfb200_als_set_profile(cmfb200_als *s, int on) { s->st.profile = on != 0; }
+
+int cmfb200_als_read_profile(cmfb200_als *s, int which, double *total_ms, long long *count)
+{
+    return s->st.read_profile(which, total_ms, count);
+}
+
 int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }
 
 long long cmfb200_als_launch_count(const cmfb200_als *s) { return s->st.launches; }

@@ -20,6 +20,7 @@
 // the slot after its k coordinates.
 #include "sweep.h"
 #include "device_utils.cuh"
+#include <cstdlib>
 
 namespace cmfb200 {
 
@@ -364,6 +365,10 @@ int launch_cfg(const CgSweepParams &p, cudaStream_t stream)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem);
     if (occ < 1) occ = 1;
     // persistent grid: a whole number of waves (SM count x resident blocks), never more blocks than slots
+    {
+        const char *e = std::getenv("CMFB200_OCC");
+        if (e && std::atoi(e) > 0 && std::atoi(e) < occ) occ = std::atoi(e);
+    }
     long long grid = (long long)sms * occ;
     if (grid > n_slots) grid = n_slots;
     kern<<<(unsigned)grid, W * 32, smem, stream>>>(p);
@@ -377,7 +382,13 @@ template <bool IMPLICIT> int dispatch(const CgSweepParams &p, cudaStream_t strea
 #ifdef USE_FLOAT
     if (kk <= 16) return launch_cfg<float, 4, 4, IMPLICIT>(p, stream);
     if (kk <= 32) return launch_cfg<float, 8, 4, IMPLICIT>(p, stream);
-    if (kk <= 64) return launch_cfg<float, 8, 8, IMPLICIT>(p, stream);
+    if (kk <= 64) {
+        const char *e = std::getenv("CMFB200_CFG64");
+        const int v = e ? std::atoi(e) : 0;
+        if (v == 1) return launch_cfg<float, 8, 8, IMPLICIT>(p, stream);
+        if (v == 2) return launch_cfg<float, 4, 16, IMPLICIT>(p, stream);
+        return launch_cfg<float, 16, 4, IMPLICIT>(p, stream);   // measured fastest: 8 entries in flight per warp
+    }
     if (kk <= 128) return launch_cfg<float, 8, 16, IMPLICIT>(p, stream);
     if (kk <= 256) return launch_cfg<float, 8, 32, IMPLICIT>(p, stream);
     if (kk <= 512) return launch_cfg<float, 16, 32, IMPLICIT>(p, stream);

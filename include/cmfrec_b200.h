@@ -205,6 +205,11 @@ int cmfb200_als_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_t
 /* same, bracketed by CUDA events recorded on the state's stream; *elapsed_ms = device time of the n_iters */
 int cmfb200_als_timed_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg,
                               int finalize_chol, float *elapsed_ms);
+/* per-launch timing of the row-solve kernel: when on, every half-sweep brackets its solve kernel with CUDA events
+ * on the state's stream; read_profile synchronises, returns the summed kernel time and launch count for
+ * which = 0 (B sweeps) / 1 (A sweeps) since the last read, and clears the record. */
+void cmfb200_als_set_profile(cmfb200_als *s, int on);
+int cmfb200_als_read_profile(cmfb200_als *s, int which, double *total_ms, long long *count);
 int cmfb200_als_sync(cmfb200_als *s);
 /* kernels launched by this state so far */
 long long cmfb200_als_launch_count(const cmfb200_als *s);

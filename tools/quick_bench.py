@@ -19,7 +19,12 @@ a = ap.parse_args()
 dt = np.dtype(np.float32 if a.dtype == "f32" else np.float64)
 L = _lib.load(dt)
 t = time.time()
-ixA, ixB, X, m, n = synth.make(a.shape, dt, a.scale)
+cache = "/tmp/cmfb200_qb_%s_%s_%g.npz" % (a.shape, a.dtype, a.scale)
+if os.path.exists(cache):
+    z = np.load(cache); ixA, ixB, X, m, n = z["a"], z["b"], z["x"], int(z["m"]), int(z["n"])
+else:
+    ixA, ixB, X, m, n = synth.make(a.shape, dt, a.scale)
+    np.savez(cache, a=ixA, b=ixB, x=X, m=m, n=n)
 print("generated %s: m=%d n=%d nnz=%d in %.1fs" % (a.shape, m, n, X.size, time.time() - t), flush=True)
 if not a.implicit:
     X = (X - X.mean()).astype(dt)
