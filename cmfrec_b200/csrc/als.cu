@@ -8,6 +8,12 @@
 
 namespace cmfb200 {
 
+static int env_or(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 static int long_row_threshold()
 {
     static int v = -1;
@@ -88,6 +94,21 @@ static int build_side(const size_t *ptr, const int_t *idx, const real_t *val, co
     while (n_long < (int_t)order.size() && hptr[order[n_long] + 1] - hptr[order[n_long]] >= thr) n_long++;
     side.n_order = (int_t)order.size();
     side.n_long = n_long;
+    {
+        const size_t t_huge = (size_t)env_or("CMFB200_HUGE_ROW", 8192);
+        int_t h = 0;
+        while (h < n_long && hptr[order[h] + 1] - hptr[order[h]] >= t_huge) h++;
+        side.n_huge = h;
+    }
+    {
+        const size_t t_big = (size_t)env_or("CMFB200_T_BIG", 512), t_mid = (size_t)env_or("CMFB200_T_MID", 96);
+        int_t a = 0, b = 0;
+        while (a < (int_t)order.size() && hptr[order[a] + 1] - hptr[order[a]] >= t_big) a++;
+        b = a;
+        while (b < (int_t)order.size() && hptr[order[b] + 1] - hptr[order[b]] >= t_mid) b++;
+        side.n_big = a;
+        side.n_mid = b;
+    }
 
     if (!side.ptr.alloc(hptr.size()) || !side.idx.alloc(std::max<size_t>(total, 1)) ||
         !side.val.alloc(std::max<size_t>(total, 1)) || !side.order.alloc(std::max<size_t>(order.size(), 1)))
@@ -107,6 +128,9 @@ AlsState::~AlsState()
     for (auto &v : sweep_events)
         for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     delete link;
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
 }
 
 int AlsState::read_profile(int which, double *total_ms, long long *count)
@@ -132,6 +156,9 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
 {
     cfg = c;
     stream = s;
+    if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
     if (cfg.kk < 1 || cfg.kk > max_supported_k()) return 2;
     if (cfg.world > 1) {
         if (!nccl_id) return 2;
@@ -245,10 +272,27 @@ int AlsState::half_sweep(int which, int iter, int solver)
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
+    const bool fork = solver == 0 && side_stream && p.plan.n_huge > 0 && !env_or("CMFB200_STAGED", 0);
+    if (fork) {
+        // the side stream may start once everything queued so far on the main stream is done
+        cudaEventRecord(ev_fork, stream);
+        cudaStreamWaitEvent(side_stream, ev_fork, 0);
+        p.side_stream = side_stream;
+    }
     if (solver == 0) {
-        rc = cfg.implicit ? launch_implicit_cg_sweep(p, stream) : launch_explicit_cg_sweep(p, stream);
+        rc = 3;
+        if (env_or("CMFB200_STAGED", 0)) {
+            rc = cfg.implicit ? launch_implicit_cg_sweep_staged(p, stream) : launch_explicit_cg_sweep_staged(p, stream);
+            if (rc == 0) launches += 2;
+        }
+        if (rc == 3) rc = cfg.implicit ? launch_implicit_cg_sweep(p, stream) : launch_explicit_cg_sweep(p, stream);
     } else {
         rc = cfg.implicit ? launch_implicit_chol_sweep(p, stream) : launch_explicit_chol_sweep(p, stream);
+    }
+    if (fork) {
+        cudaEventRecord(ev_join, side_stream);
+        cudaStreamWaitEvent(stream, ev_join, 0);
+        launches += 1;
     }
     if (profile) {
         cudaEventRecord(e1, stream);

@@ -40,9 +40,9 @@ struct DeviceSide {
     DevBuf<int_t> idx;
     DevBuf<real_t> val;
     DevBuf<int_t> order;
-    int_t n_order = 0, n_long = 0;
+    int_t n_order = 0, n_long = 0, n_huge = 0, n_big = 0, n_mid = 0;
     CsrView view() const { return CsrView{ptr.p, idx.p, val.p}; }
-    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long}; }
+    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long, n_huge, n_big, n_mid}; }
 };
 
 struct Renumbering {              // old (caller) row id <-> device row id
@@ -68,6 +68,8 @@ class AlsState {
 public:
     AlsConfig cfg;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // long-row kernel runs here, fenced by the two events below
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Renumbering renA, renB;
     DeviceSide byA, byB;          // byA: rows = users (CSR); byB: rows = items (CSC)
     int ldA = 0, ldB = 0;

@@ -1,0 +1,274 @@
+// The conjugate-gradient solve of ONE factor row by a team of TW warps, independent of where the opposing
+// rows come from.  The source of the row's stored entries is a policy object ("Gather") with one method
+//
+//     template <int KIND> void pass(const T (&vec)[C], T vecb, T (&acc)[C], T &accb);
+//
+// which must add, for every stored entry e of the row,   coef_e * g_e  into acc  and  coef_e  into accb,
+// where g_e is the opposing row of entry e (this lane's C coordinates of it), d_e = <g_e, vec> + vecb and
+// coef_e = entry_coef<KIND>(d_e, x_e).  Two policies exist: direct gathers from global memory / L2
+// (sweep_cg.cu) and rows staged in shared memory by bulk async copies (sweep_cg_staged.cu).
+//
+// Arithmetic: reference factors_explicit_cg (src/common.c:1098-1188) and factors_implicit_cg
+// (src/common.c:1914-1986); see sweep_cg.cu for the full list of reproduced details.
+#pragma once
+#include "sweep.h"
+#include "device_utils.cuh"
+#include <cooperative_groups.h>
+
+namespace cmfb200 {
+
+template <typename T, int C, int L> struct Layout {
+    static constexpr int VN = (C % VecOf<T>::N == 0) ? VecOf<T>::N : 1;
+    static constexpr int KP = C * L;  // padded number of coordinates handled by a group
+    // column owned by lane-in-group l, register j
+    __device__ __forceinline__ static int col(int l, int j) { return ((j / VN) * L + l) * VN + (j % VN); }
+};
+
+enum PassKind { kExplicitResidual = 0, kExplicitAp = 1, kImplicitResidual = 2, kImplicitAp = 3 };
+
+// x is the stored value (explicit: already reduced by the opposing bias), d the current prediction
+template <int KIND, typename T> __device__ __forceinline__ T entry_coef(T d, T x)
+{
+    if constexpr (KIND == kExplicitResidual) return x - d;
+    else if constexpr (KIND == kExplicitAp) return d;
+    else if constexpr (KIND == kImplicitResidual) return -(d - T(1)) * x - d;
+    else return d * (x - T(1)) + d;
+}
+
+template <int TW> __device__ __forceinline__ void team_barrier(int bar_id)
+{
+    if constexpr (TW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(TW * 32) : "memory");
+}
+
+// Shared-memory scratch of one team: reduction buffer [2][TW][KP+4] (TW > 1 only) and the broadcast vector
+// [KP] used by the implicit model's Gram product.
+template <typename T, int C, int L, int TW> struct TeamScratch {
+    static constexpr int KP = Layout<T, C, L>::KP;
+    static constexpr int RED_STRIDE = KP + 4;
+    static constexpr int elems() { return (TW > 1 ? 2 * TW * RED_STRIDE : 0) + KP; }
+};
+
+// CL > 1: the team spans the CL thread blocks of a cluster (TW warps in each); per-pass totals are then also
+// combined across the blocks through distributed shared memory (`cl_buf`, [2][KP+4] in every block).
+template <typename T, int C, int L, bool IMPLICIT, int TW, bool GRAM_SMEM, int CL = 1> struct CgRow {
+    typedef Layout<T, C, L> Lay;
+    typedef TeamScratch<T, C, L, TW> Scr;
+    static constexpr int G = 32 / L;
+
+    const CgSweepParams &p;
+    T *red;          // [2][TW][RED_STRIDE]
+    T *vec_sm;       // [KP]
+    const T *gram;   // shared-memory copy (row stride KP) or global (row stride kk)
+    int lane, wt, g, l, bar_id;
+    int phase;
+    T *cl_buf = nullptr;   // CL > 1 only
+    int cl_phase = 0;
+    int cl_rank = 0;       // rank of this block in the cluster (CL > 1)
+
+    __device__ __forceinline__ CgRow(const CgSweepParams &p_, T *scratch, const T *gram_, int warp_in_team, int bar_id_)
+        : p(p_), red(scratch), vec_sm(scratch + (TW > 1 ? 2 * TW * Scr::RED_STRIDE : 0)), gram(gram_), wt(warp_in_team),
+          bar_id(bar_id_), phase(0)
+    {
+        lane = threadIdx.x & 31;
+        g = lane / L;
+        l = lane % L;
+    }
+
+    __device__ __forceinline__ void sync() const { team_barrier<TW>(bar_id); }
+
+    // partial sums held by every lane -> totals in every lane of the team
+    __device__ __forceinline__ void combine(T (&acc)[C], T &accb)
+    {
+#pragma unroll
+        for (int j = 0; j < C; j++) acc[j] = across_groups_sum<L>(acc[j]);
+        accb = across_groups_sum<L>(accb);
+        if constexpr (TW > 1) {
+            T *buf = red + phase * (TW * Scr::RED_STRIDE);
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < C; j++) buf[wt * Scr::RED_STRIDE + Lay::col(l, j)] = acc[j];
+                if (l == 0) buf[wt * Scr::RED_STRIDE + Lay::KP] = accb;
+            }
+            sync();
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                T s = T(0);
+#pragma unroll
+                for (int ww = 0; ww < TW; ww++) s += buf[ww * Scr::RED_STRIDE + Lay::col(l, j)];
+                acc[j] = s;
+            }
+            T sb = T(0);
+#pragma unroll
+            for (int ww = 0; ww < TW; ww++) sb += buf[ww * Scr::RED_STRIDE + Lay::KP];
+            accb = sb;
+            phase ^= 1;
+        }
+        if constexpr (CL > 1) {
+            namespace cg = cooperative_groups;
+            cg::cluster_group cluster = cg::this_cluster();
+            T *mine = cl_buf + cl_phase * Scr::RED_STRIDE;
+            if (g == 0 && wt == 0) {
+#pragma unroll
+                for (int j = 0; j < C; j++) mine[Lay::col(l, j)] = acc[j];
+                if (l == 0) mine[Lay::KP] = accb;
+            }
+            cluster.sync();
+#pragma unroll
+            for (int j = 0; j < C; j++) acc[j] = T(0);
+            accb = T(0);
+            for (int r = 0; r < CL; r++) {
+                const T *peer = cluster.map_shared_rank(mine, r);
+#pragma unroll
+                for (int j = 0; j < C; j++) acc[j] += peer[Lay::col(l, j)];
+                accb += peer[Lay::KP];
+            }
+            cl_phase ^= 1;
+        }
+    }
+
+    __device__ __forceinline__ T dot_full(const T (&x)[C], const T (&y)[C], T xb, T yb) const
+    {
+        T s0 = T(0), s1 = T(0);
+#pragma unroll
+        for (int j = 0; j < C; j += 2) {
+            s0 = fma(x[j], y[j], s0);
+            if (j + 1 < C) s1 = fma(x[j + 1], y[j + 1], s1);
+        }
+        T s = group_sum<L>(s0 + s1);
+        return fma(xb, yb, s);
+    }
+
+    // acc += sign * gram * vec, rows of gram distributed over the groups of the team
+    __device__ __forceinline__ void gram_matvec(const T (&vec)[C], T sign, T (&acc)[C])
+    {
+        const int kk = p.kk;
+        sync();  // previous readers of vec_sm are done
+        if (g == 0 && wt == 0) {
+#pragma unroll
+            for (int j = 0; j < C; j++) vec_sm[Lay::col(l, j)] = vec[j];
+        }
+        sync();
+        const int ngroups = CL * TW * G;
+        const int gg = (cl_rank * TW + wt) * G + g;
+        for (int d = gg; d < kk; d += ngroups) {
+            const T s = sign * vec_sm[d];
+            if constexpr (GRAM_SMEM) {
+                const T *mrow = gram + (size_t)d * Lay::KP;
+#pragma unroll
+                for (int j = 0; j < C; j++) acc[j] = fma(mrow[Lay::col(l, j)], s, acc[j]);
+            } else {
+                const T *mrow = gram + (size_t)d * kk;
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int c = Lay::col(l, j);
+                    if (c < kk) acc[j] = fma(__ldg(mrow + c), s, acc[j]);
+                }
+            }
+        }
+    }
+
+    // Solve one row with at least one stored entry.  `gather` is positioned on that row.
+    template <typename Gather> __device__ void solve(int row, int nnz, Gather &gather)
+    {
+        const int kk = p.kk;
+        T *frow = p.F + (size_t)row * (size_t)p.ldF;
+
+        T a[C], r[C], pv[C], acc[C];
+        T ab = T(0), rb = T(0), pb = T(0), accb = T(0);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int c = Lay::col(l, j);
+            a[j] = (c < kk) ? frow[c] : T(0);
+        }
+        const bool hb = !IMPLICIT && p.solve_bias;
+        if (hb) ab = p.bias_start_one ? T(1) : frow[kk];
+
+        T lam = p.lam, lam_last = p.lam_last;
+        if (!IMPLICIT && p.scale_lam) {
+            lam *= (T)nnz;
+            if (!p.scale_bias_const) lam_last *= (T)nnz;
+        }
+
+        // ---- residual at the starting point
+#pragma unroll
+        for (int j = 0; j < C; j++) acc[j] = T(0);
+        accb = T(0);
+        if constexpr (IMPLICIT) gram_matvec(a, T(-1), acc);
+        gather.template pass<IMPLICIT ? kImplicitResidual : kExplicitResidual>(a, ab, acc, accb);
+        combine(acc, accb);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int c = Lay::col(l, j);
+            r[j] = (c < kk) ? fma(-lam, a[j], acc[j]) : T(0);
+        }
+        if (hb) {
+            rb = fma(-lam, ab, accb);
+            if (lam != lam_last) rb -= (lam_last - lam) * ab;
+        }
+        T r_old = dot_full(r, r, rb, rb);
+        bool changed = false;
+        if (!(r_old <= T(1e-12))) {
+#pragma unroll
+            for (int j = 0; j < C; j++) pv[j] = r[j];
+            pb = rb;
+            for (int step = 0; step < p.max_cg_steps; step++) {
+#pragma unroll
+                for (int j = 0; j < C; j++) acc[j] = T(0);
+                accb = T(0);
+                if constexpr (IMPLICIT) gram_matvec(pv, T(1), acc);
+                gather.template pass<IMPLICIT ? kImplicitAp : kExplicitAp>(pv, pb, acc, accb);
+                combine(acc, accb);
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int c = Lay::col(l, j);
+                    acc[j] = (c < kk) ? fma(lam, pv[j], acc[j]) : T(0);
+                }
+                if (hb) {
+                    accb = fma(lam, pb, accb);
+                    if (lam != lam_last) accb += (lam_last - lam) * pb;
+                } else {
+                    accb = T(0);
+                }
+                const T alpha = r_old / dot_full(pv, acc, pb, accb);
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    a[j] = fma(alpha, pv[j], a[j]);
+                    r[j] = fma(-alpha, acc[j], r[j]);
+                }
+                ab = fma(alpha, pb, ab);
+                rb = fma(-alpha, accb, rb);
+                changed = true;
+                const T r_new = dot_full(r, r, rb, rb);
+                if (r_new <= T(1e-8)) break;
+                const T beta = r_new / r_old;
+#pragma unroll
+                for (int j = 0; j < C; j++) pv[j] = fma(beta, pv[j], r[j]);
+                pb = fma(beta, pb, rb);
+                r_old = r_new;
+            }
+        }
+        // A row that exits before the first step is left exactly as it was, except that a bias coordinate
+        // restarted from 1.0 is what the reference leaves in the matrix.
+        if (g == 0 && wt == 0 && cl_rank == 0) {
+            if (changed) {
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int c = Lay::col(l, j);
+                    if (c < kk) frow[c] = a[j];
+                }
+            }
+            if (hb && l == 0 && (changed || p.bias_start_one)) frow[kk] = ab;
+        }
+    }
+
+    // rows without entries are skipped by the reference and keep whatever their storage holds, which for the
+    // bias column is the 1.0 written there before the sweep (src/collective.c:8538-8542)
+    __device__ __forceinline__ void empty_row(int row) const
+    {
+        if (!IMPLICIT && p.solve_bias && p.bias_start_one && lane == 0 && wt == 0)
+            p.F[(size_t)row * (size_t)p.ldF + p.kk] = T(1);
+    }
+};
+
+}  // namespace cmfb200

@@ -21,6 +21,8 @@ struct SweepPlan {          // device pointers, built once per CSR by build_swee
     const int_t *order;     // rows sorted by decreasing degree (rows without entries excluded)
     int_t n_rows;           // length of order
     int_t n_long;           // the first n_long rows of order get one whole thread block each
+    int_t n_huge;           // the first n_huge (<= n_long) rows get a whole cluster of thread blocks each
+    int_t n_big, n_mid;     // staged kernel: rows [0,n_big) -> 16-warp teams, [n_big,n_mid) -> 4-warp teams, rest 1 warp
 };
 
 struct CgSweepParams {
@@ -36,11 +38,17 @@ struct CgSweepParams {
     bool bias_start_one;          // start the bias coordinate from 1.0 instead of the stored bias
     int max_cg_steps;
     const real_t *gram;           // implicit only: G^T G, [kk x kk] row-major, full symmetric
+    cudaStream_t side_stream;     // optional second stream for the long-row kernel (caller orders it around the sweep)
 };
 
 // returns 0, or 2 when kk is outside the supported range
 int launch_explicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream);
 int launch_implicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream);
+
+// Same sweeps with the gathered rows staged in shared memory by bulk async copies (sweep_cg_staged.cu).
+// Return 3 when the shape is not covered (nothing was launched): use the direct variant above.
+int launch_explicit_cg_sweep_staged(const CgSweepParams &p, cudaStream_t stream);
+int launch_implicit_cg_sweep_staged(const CgSweepParams &p, cudaStream_t stream);
 
 // Exact per-row solves (normal equations + Cholesky); same parameter block, `max_cg_steps` and
 // `bias_start_one` only matter for rows without entries.  reference: factors_closed_form sparse branch

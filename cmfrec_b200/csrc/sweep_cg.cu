@@ -18,8 +18,7 @@
 // side's bias from x, which the reference does by rewriting the CSR values before every half-sweep
 // (src/collective.c:8566-8571, 8750-8755), is fused into the gather: the opposing row carries its bias in
 // the slot after its k coordinates.
-#include "sweep.h"
-#include "device_utils.cuh"
+#include "cg_row.cuh"
 #include <cstdlib>
 
 namespace cmfb200 {
@@ -27,13 +26,6 @@ namespace cmfb200 {
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
-
-template <typename T, int C, int L> struct Layout {
-    static constexpr int VN = (C % VecOf<T>::N == 0) ? VecOf<T>::N : 1;
-    static constexpr int KP = C * L;  // padded number of coordinates handled by a group
-    // column owned by lane-in-group l, register j
-    __device__ __forceinline__ static int col(int l, int j) { return ((j / VN) * L + l) * VN + (j % VN); }
-};
 
 // fetch this lane's C coordinates of one opposing row (columns >= ld read as zero)
 template <typename T, int C, int L>
@@ -60,83 +52,29 @@ __device__ __forceinline__ void gather_row(const T *row, int l, int ld, bool val
     }
 }
 
-enum PassKind { kExplicitResidual = 0, kExplicitAp = 1, kImplicitResidual = 2, kImplicitAp = 3 };
-
-template <typename T, int C, int L, bool IMPLICIT, bool TEAM, bool GRAM_SMEM> struct RowSolver {
-    typedef Layout<T, C, L> Lay;
+// Entries of the row read straight from global memory (L2 for the opposing factor): every pass re-gathers.
+// The team's warps take 32-entry chunks round-robin; inside a warp each of the 32/L groups owns one entry at a time.
+template <typename T, int C, int L, int TW> struct DirectGather {
     static constexpr int G = 32 / L;
-    static constexpr int W = kWarpsPerBlock;
-    static constexpr int RED_STRIDE = Lay::KP + 4;
-
     const CgSweepParams &p;
-    T *red;          // TEAM: [2][W][RED_STRIDE]
-    T *vec_sm;       // implicit: KP entries, per team (TEAM) or per warp
-    const T *gram;   // implicit: shared-memory copy (row stride KP) or global (row stride kk)
-    int lane, w, g, l;
-    int phase;
+    size_t beg;
+    int nnz, lane, wt, g, l;
+    int first_chunk, chunk_stride;   // which 32-entry chunks this warp takes
 
-    __device__ __forceinline__ RowSolver(const CgSweepParams &p_, T *red_, T *vec_sm_, const T *gram_)
-        : p(p_), red(red_), vec_sm(vec_sm_), gram(gram_), phase(0)
+    __device__ __forceinline__ DirectGather(const CgSweepParams &p_, int warp_in_team)
+        : p(p_), beg(0), nnz(0), wt(warp_in_team), first_chunk(warp_in_team), chunk_stride(TW)
     {
         lane = threadIdx.x & 31;
-        w = threadIdx.x >> 5;
         g = lane / L;
         l = lane % L;
     }
 
-    __device__ __forceinline__ void team_sync() const
-    {
-        if constexpr (TEAM) __syncthreads(); else __syncwarp();
-    }
-
-    // acc[j] (and accb) hold this lane's partial sums over the entries its group processed; on return every
-    // lane of the team holds the totals.
-    __device__ __forceinline__ void combine(T (&acc)[C], T &accb)
-    {
-#pragma unroll
-        for (int j = 0; j < C; j++) acc[j] = across_groups_sum<L>(acc[j]);
-        accb = across_groups_sum<L>(accb);
-        if constexpr (TEAM) {
-            T *buf = red + phase * (W * RED_STRIDE);
-            if (g == 0) {
-#pragma unroll
-                for (int j = 0; j < C; j++) buf[w * RED_STRIDE + Lay::col(l, j)] = acc[j];
-                if (l == 0) buf[w * RED_STRIDE + Lay::KP] = accb;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < C; j++) {
-                T s = T(0);
-#pragma unroll
-                for (int ww = 0; ww < W; ww++) s += buf[ww * RED_STRIDE + Lay::col(l, j)];
-                acc[j] = s;
-            }
-            T sb = T(0);
-#pragma unroll
-            for (int ww = 0; ww < W; ww++) sb += buf[ww * RED_STRIDE + Lay::KP];
-            accb = sb;
-            phase ^= 1;
-        }
-    }
-
-    __device__ __forceinline__ T dot_full(const T (&x)[C], const T (&y)[C], T xb, T yb) const
-    {
-        T s = T(0);
-#pragma unroll
-        for (int j = 0; j < C; j++) s = fma(x[j], y[j], s);
-        s = group_sum<L>(s);
-        return fma(xb, yb, s);
-    }
-
-    // one pass over the stored entries of the row: acc += sum_e coef_e * g_e, accb += sum_e coef_e
     template <int KIND>
-    __device__ __forceinline__ void sparse_pass(size_t beg, int nnz, const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
+    __device__ __forceinline__ void pass(const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
     {
         const int nchunks = (nnz + 31) >> 5;
-        const int first = TEAM ? w : 0;
-        const int stride = TEAM ? W : 1;
         const int kk = p.kk;
-        for (int ch = first; ch < nchunks; ch += stride) {
+        for (int ch = first_chunk; ch < nchunks; ch += chunk_stride) {
             const int e = ch * 32 + lane;
             int col_r = -1;
             T x_r = T(0);
@@ -150,160 +88,27 @@ template <typename T, int C, int L, bool IMPLICIT, bool TEAM, bool GRAM_SMEM> st
                 if (t * G >= left) break;  // warp-uniform
                 const int item = t * G + g;
                 const int col = __shfl_sync(CMF_FULL_MASK, col_r, item);
-                const T x = __shfl_sync(CMF_FULL_MASK, x_r, item);
+                T x = __shfl_sync(CMF_FULL_MASK, x_r, item);
                 const bool valid = col >= 0;
                 const T *grow = p.G + (size_t)(valid ? col : 0) * (size_t)p.ldG;
                 T v[C];
                 gather_row<T, C, L>(grow, l, p.ldG, valid, v);
-                T ob = T(0);
-                if (p.center_opp && valid) ob = __ldg(grow + kk);
-                T d = T(0);
+                if (p.center_opp && valid) x -= __ldg(grow + kk);
+                T d0 = T(0), d1 = T(0);
 #pragma unroll
-                for (int j = 0; j < C; j++) d = fma(v[j], vec[j], d);
-                d = group_sum<L>(d);
+                for (int j = 0; j < C; j += 2) {
+                    d0 = fma(v[j], vec[j], d0);
+                    if (j + 1 < C) d1 = fma(v[j + 1], vec[j + 1], d1);
+                }
+                T d = group_sum<L>(d0 + d1);
                 d += vecb;  // opposing value of the bias coordinate is 1 (vecb is 0 when there is none)
-                T coef;
-                if constexpr (KIND == kExplicitResidual) coef = (x - ob) - d;
-                else if constexpr (KIND == kExplicitAp) coef = d;
-                else if constexpr (KIND == kImplicitResidual) coef = -(d - T(1)) * x - d;
-                else coef = d * (x - T(1)) + d;
+                T coef = entry_coef<KIND>(d, x);
                 if (!valid) coef = T(0);
 #pragma unroll
                 for (int j = 0; j < C; j++) acc[j] = fma(coef, v[j], acc[j]);
                 accb += coef;
             }
         }
-    }
-
-    // acc += sign * gram * vec, rows of gram distributed over the groups of the team
-    __device__ __forceinline__ void gram_matvec(const T (&vec)[C], T sign, T (&acc)[C])
-    {
-        const int kk = p.kk;
-        team_sync();  // previous readers of vec_sm are done
-        if (g == 0 && (!TEAM || w == 0)) {
-#pragma unroll
-            for (int j = 0; j < C; j++) vec_sm[Lay::col(l, j)] = vec[j];
-        }
-        team_sync();
-        const int ngroups = TEAM ? W * G : G;
-        const int gg = TEAM ? w * G + g : g;
-        for (int d = gg; d < kk; d += ngroups) {
-            const T s = sign * vec_sm[d];
-            if constexpr (GRAM_SMEM) {
-                const T *mrow = gram + (size_t)d * Lay::KP;
-#pragma unroll
-                for (int j = 0; j < C; j++) acc[j] = fma(mrow[Lay::col(l, j)], s, acc[j]);
-            } else {
-                const T *mrow = gram + (size_t)d * kk;
-#pragma unroll
-                for (int j = 0; j < C; j++) {
-                    const int c = Lay::col(l, j);
-                    if (c < kk) acc[j] = fma(__ldg(mrow + c), s, acc[j]);
-                }
-            }
-        }
-    }
-
-    __device__ void solve(int row)
-    {
-        const size_t beg = p.X.ptr[row];
-        const int nnz = (int)(p.X.ptr[row + 1] - beg);
-        const int kk = p.kk;
-        T *frow = p.F + (size_t)row * (size_t)p.ldF;
-        if (nnz <= 0) {
-            // rows without entries are skipped by the reference and keep whatever their storage holds, which
-            // for the bias column is the 1.0 written there before the sweep (src/collective.c:8538-8542)
-            if (!IMPLICIT && p.solve_bias && p.bias_start_one && lane == 0 && (!TEAM || w == 0)) frow[kk] = T(1);
-            return;
-        }
-
-        T a[C], r[C], pv[C], acc[C];
-        T ab = T(0), rb = T(0), pb = T(0), accb = T(0);
-#pragma unroll
-        for (int j = 0; j < C; j++) {
-            const int c = Lay::col(l, j);
-            a[j] = (c < kk) ? frow[c] : T(0);
-        }
-        const bool hb = !IMPLICIT && p.solve_bias;
-        if (hb) ab = p.bias_start_one ? T(1) : frow[kk];
-
-        T lam = p.lam, lam_last = p.lam_last;
-        if (!IMPLICIT && p.scale_lam) {
-            lam *= (T)nnz;
-            if (!p.scale_bias_const) lam_last *= (T)nnz;
-        }
-
-        // ---- residual at the starting point
-#pragma unroll
-        for (int j = 0; j < C; j++) acc[j] = T(0);
-        accb = T(0);
-        if constexpr (IMPLICIT) gram_matvec(a, T(-1), acc);
-        sparse_pass<IMPLICIT ? kImplicitResidual : kExplicitResidual>(beg, nnz, a, ab, acc, accb);
-        combine(acc, accb);
-#pragma unroll
-        for (int j = 0; j < C; j++) {
-            const int c = Lay::col(l, j);
-            r[j] = (c < kk) ? fma(-lam, a[j], acc[j]) : T(0);
-        }
-        if (hb) {
-            rb = fma(-lam, ab, accb);
-            if (lam != lam_last) rb -= (lam_last - lam) * ab;
-        }
-        T r_old = dot_full(r, r, rb, rb);
-        bool changed = false;
-        if (!(r_old <= T(1e-12))) {
-#pragma unroll
-            for (int j = 0; j < C; j++) pv[j] = r[j];
-            pb = rb;
-            for (int step = 0; step < p.max_cg_steps; step++) {
-#pragma unroll
-                for (int j = 0; j < C; j++) acc[j] = T(0);
-                accb = T(0);
-                if constexpr (IMPLICIT) gram_matvec(pv, T(1), acc);
-                sparse_pass<IMPLICIT ? kImplicitAp : kExplicitAp>(beg, nnz, pv, pb, acc, accb);
-                combine(acc, accb);
-#pragma unroll
-                for (int j = 0; j < C; j++) {
-                    const int c = Lay::col(l, j);
-                    acc[j] = (c < kk) ? fma(lam, pv[j], acc[j]) : T(0);
-                }
-                if (hb) {
-                    accb = fma(lam, pb, accb);
-                    if (lam != lam_last) accb += (lam_last - lam) * pb;
-                } else {
-                    accb = T(0);
-                }
-                const T alpha = r_old / dot_full(pv, acc, pb, accb);
-#pragma unroll
-                for (int j = 0; j < C; j++) {
-                    a[j] = fma(alpha, pv[j], a[j]);
-                    r[j] = fma(-alpha, acc[j], r[j]);
-                }
-                ab = fma(alpha, pb, ab);
-                rb = fma(-alpha, accb, rb);
-                changed = true;
-                const T r_new = dot_full(r, r, rb, rb);
-                if (r_new <= T(1e-8)) break;
-                const T beta = r_new / r_old;
-#pragma unroll
-                for (int j = 0; j < C; j++) pv[j] = fma(beta, pv[j], r[j]);
-                pb = fma(beta, pb, rb);
-                r_old = r_new;
-            }
-        }
-        // A row that exits before the first step is left exactly as it was, except that a bias coordinate
-        // restarted from 1.0 is what the reference leaves in the matrix.
-        if (g == 0 && (!TEAM || w == 0)) {
-            if (changed) {
-#pragma unroll
-                for (int j = 0; j < C; j++) {
-                    const int c = Lay::col(l, j);
-                    if (c < kk) frow[c] = a[j];
-                }
-            }
-            if (hb && l == 0 && (changed || p.bias_start_one)) frow[kk] = ab;
-        }
-        if constexpr (TEAM) __syncthreads();
     }
 };
 
@@ -313,9 +118,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgS
     typedef Layout<T, C, L> Lay;
     constexpr int W = kWarpsPerBlock;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *red = reinterpret_cast<T *>(smem_raw);                                  // [2][W][KP+4]
-    T *vec_sm = red + 2 * W * (Lay::KP + 4);                                   // [W][KP]
-    T *gram_sm = vec_sm + W * Lay::KP;                                         // [kk][KP] (implicit, if it fits)
+    T *scratch_team = reinterpret_cast<T *>(smem_raw);                         // block-per-row scratch
+    T *scratch_warp = scratch_team + TeamScratch<T, C, L, W>::elems();         // [W] warp-per-row scratch
+    T *gram_sm = scratch_warp + W * TeamScratch<T, C, L, 1>::elems();          // [kk][KP] (implicit, if it fits)
     const T *gram = p.gram;
     if constexpr (IMPLICIT && GRAM_SMEM) {
         const int kk = p.kk;
@@ -332,24 +137,108 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgS
     const int n_slots = n_long + n_short_slots;
     for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
         if (slot < n_long) {
-            RowSolver<T, C, L, IMPLICIT, true, GRAM_SMEM> s(p, red, vec_sm, gram);
-            s.solve(p.plan.order[slot]);
+            // whole block on one row
+            const int row = p.plan.order[slot];
+            const size_t beg = p.X.ptr[row];
+            const int nnz = (int)(p.X.ptr[row + 1] - beg);
+            CgRow<T, C, L, IMPLICIT, W, GRAM_SMEM> s(p, scratch_team, gram, w, 0);
+            if (nnz > 0) {
+                DirectGather<T, C, L, W> gat(p, w);
+                gat.beg = beg; gat.nnz = nnz;
+                s.solve(row, nnz, gat);
+            } else {
+                s.empty_row(row);
+            }
+            __syncthreads();
         } else {
             const int i = n_long + (slot - n_long) * W + w;
             if (i < p.plan.n_rows) {
-                RowSolver<T, C, L, IMPLICIT, false, GRAM_SMEM> s(p, red, vec_sm + w * Lay::KP, gram);
-                s.solve(p.plan.order[i]);
+                const int row = p.plan.order[i];
+                const size_t beg = p.X.ptr[row];
+                const int nnz = (int)(p.X.ptr[row + 1] - beg);
+                CgRow<T, C, L, IMPLICIT, 1, GRAM_SMEM> s(p, scratch_warp + w * TeamScratch<T, C, L, 1>::elems(), gram, 0, 0);
+                if (nnz > 0) {
+                    DirectGather<T, C, L, 1> gat(p, 0);
+                    gat.beg = beg; gat.nnz = nnz;
+                    s.solve(row, nnz, gat);
+                } else {
+                    s.empty_row(row);
+                }
             }
         }
     }
 }
 
+// Rows with very many stored entries: one row per CLUSTER of kClusterSize thread blocks, so that the longest
+// rows do not leave the rest of the GPU idle at the end of the sweep.  Entries are dealt over all warps of the
+// cluster; the per-pass sums are combined through distributed shared memory (cg_row.cuh, CL > 1).
+constexpr int kClusterSize = 8;
+
 template <typename T, int C, int L, bool IMPLICIT>
-int launch_cfg(const CgSweepParams &p, cudaStream_t stream)
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kWarpsPerBlock * 32)
+    cg_sweep_cluster_kernel(const CgSweepParams p, int n_huge)
 {
+    namespace cg = cooperative_groups;
+    constexpr int W = kWarpsPerBlock;
+    typedef TeamScratch<T, C, L, W> Scr;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw);
+    T *cl_buf = scratch + Scr::elems();                 // [2][RED_STRIDE]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int w = threadIdx.x >> 5;
+    const int n_clusters = gridDim.x / kClusterSize;
+    for (int slot = blockIdx.x / kClusterSize; slot < n_huge; slot += n_clusters) {
+        const int row = p.plan.order[slot];
+        const size_t beg = p.X.ptr[row];
+        const int nnz = (int)(p.X.ptr[row + 1] - beg);
+        CgRow<T, C, L, IMPLICIT, W, false, kClusterSize> s(p, scratch, p.gram, w, 0);
+        s.cl_buf = cl_buf;
+        DirectGather<T, C, L, W> gat(p, w);
+        gat.beg = beg; gat.nnz = nnz;
+        gat.first_chunk = rank * W + w;
+        gat.chunk_stride = kClusterSize * W;
+        s.cl_rank = rank;   // only block 0 of the cluster writes the row back
+        s.solve(row, nnz, gat);
+        cluster.sync();
+    }
+}
+
+template <typename T, int C, int L, bool IMPLICIT>
+int launch_cluster_cfg(const CgSweepParams &p, int n_huge, cudaStream_t stream)
+{
+    if (n_huge <= 0) return 0;
+    constexpr int W = kWarpsPerBlock;
+    typedef TeamScratch<T, C, L, W> Scr;
+    const size_t smem = (size_t)(Scr::elems() + 2 * Scr::RED_STRIDE) * sizeof(T);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int clusters = n_huge;
+    const int max_clusters = 2 * (sms / kClusterSize);
+    if (clusters > max_clusters) clusters = max_clusters;
+    auto kern = cg_sweep_cluster_kernel<T, C, L, IMPLICIT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<clusters * kClusterSize, W * 32, smem, stream>>>(p, n_huge);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+template <typename T, int C, int L, bool IMPLICIT>
+int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
+{
+    // the first n_huge rows of the (degree-sorted) order go to the cluster kernel, the rest to the main kernel
+    CgSweepParams p = p_in;
+    int n_huge = p.plan.n_huge < p.plan.n_long ? p.plan.n_huge : p.plan.n_long;
+    if (n_huge > 0) {
+        int rc = launch_cluster_cfg<T, C, L, IMPLICIT>(p_in, n_huge, p_in.side_stream ? p_in.side_stream : stream);
+        if (rc) return rc;
+        p.plan.order += n_huge;
+        p.plan.n_rows -= n_huge;
+        p.plan.n_long -= n_huge;
+    }
     typedef Layout<T, C, L> Lay;
     constexpr int W = kWarpsPerBlock;
-    size_t smem = (size_t)(2 * W * (Lay::KP + 4) + W * Lay::KP) * sizeof(T);
+    size_t smem = (size_t)(TeamScratch<T, C, L, W>::elems() + W * TeamScratch<T, C, L, 1>::elems()) * sizeof(T);
     const size_t gram_bytes = IMPLICIT ? (size_t)p.kk * Lay::KP * sizeof(T) : 0;
     const bool gram_in_smem = IMPLICIT && (smem + gram_bytes <= 100 * 1024);
     if (gram_in_smem) smem += gram_bytes;

