@@ -112,7 +112,7 @@ REFERENCE_ENTRY_POINTS = ("fit_collective_explicit_als", "fit_collective_implici
 
 PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
     "cmfb200_real_name", "cmfb200_device_count", "cmfb200_random_init", "cmfb200_coo_to_csr_and_csc",
-    "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_nccl_unique_id", "cmfb200_als_create",
+    "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_partition_rows", "cmfb200_nccl_unique_id", "cmfb200_als_create",
     "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
     "cmfb200_als_iterate", "cmfb200_als_timed_iterate", "cmfb200_als_set_profile",
     "cmfb200_als_read_profile", "cmfb200_als_sync", "cmfb200_als_launch_count", "cmfb200_als_local_counts",
@@ -151,6 +151,8 @@ def bind_product(lib, dtype):
     lib.cmfb200_global_mean.argtypes = [P, c_size_t, c_int]
     lib.cmfb200_init_biases_twosided.restype = None
     lib.cmfb200_init_biases_twosided.argtypes = [c_int, c_int, P, P, P, P, P, P, real, real, c_bool, c_bool, P, P, c_int]
+    lib.cmfb200_partition_rows.restype = c_int
+    lib.cmfb200_partition_rows.argtypes = [P, c_int, c_int, P, C.POINTER(c_int)]
     lib.cmfb200_nccl_unique_id.restype = c_int
     lib.cmfb200_nccl_unique_id.argtypes = [P]
     lib.AlsOptions = als_options_type(real)

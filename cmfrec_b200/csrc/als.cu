@@ -28,7 +28,7 @@ static int long_row_threshold()
 // Rows are dealt to ranks round-robin in order of decreasing degree, so that every rank gets the same
 // number of rows (equal-sized all-gather blocks) and nearly the same number of stored entries.
 // With one rank the numbering is left untouched.
-static void build_renumbering(const size_t *ptr, int_t rows, int world, Renumbering &ren)
+void build_renumbering(const size_t *ptr, int_t rows, int world, Renumbering &ren)
 {
     ren.block = (rows + world - 1) / world;
     ren.rows_padded = ren.block * world;

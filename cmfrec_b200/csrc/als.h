@@ -62,6 +62,9 @@ struct AlsConfig {
     int rank = 0, world = 1;
 };
 
+// deal rows to `world` ranks (round-robin over decreasing degree); identity when world == 1
+void build_renumbering(const size_t *ptr, int_t rows, int world, Renumbering &ren);
+
 class NcclLink;
 
 class AlsState {

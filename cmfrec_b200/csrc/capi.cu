@@ -124,6 +124,16 @@ void cmfb200_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const i
                          biasB, nthreads);
 }
 
+int cmfb200_partition_rows(const size_t *indptr, int_t rows, int world, int_t *to_device_row, int_t *block)
+{
+    if (!indptr || rows < 0 || world < 1 || !to_device_row) return 2;
+    Renumbering ren;
+    build_renumbering(indptr, rows, world, ren);
+    for (int_t r = 0; r < rows; r++) to_device_row[r] = ren.to_dev[r];
+    if (block) *block = ren.block;
+    return 0;
+}
+
 int cmfb200_nccl_unique_id(void *out128) { return NcclLink::unique_id(out128); }
 
 int cmfb200_als_create(cmfb200_als **out, const cmfb200_als_options *opt, const size_t *csr_p, const int_t *csr_i,

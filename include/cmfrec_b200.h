@@ -188,6 +188,11 @@ typedef struct cmfb200_als_options {
 
 int cmfb200_nccl_unique_id(void *out128);
 
+/* How rows are dealt to ranks: row r of the caller's numbering lives at device row to_device_row[r]; rank q owns
+ * device rows [q*block, (q+1)*block).  Rows are dealt round-robin in order of decreasing number of stored entries
+ * (equal block sizes, near-equal entry counts); identity when world == 1.  Pure host function. */
+int cmfb200_partition_rows(const size_t *indptr, int_t rows, int world, int_t *to_device_row, int_t *block);
+
 /* X given as CSR and CSC with identical entries (values already centred / scaled the way the model wants) */
 int cmfb200_als_create(cmfb200_als **out, const cmfb200_als_options *opt,
                        const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
