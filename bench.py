@@ -323,6 +323,7 @@ def main():
                 run = lambda nit: fit_explicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
                                                niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu)
             run(1)
+            run(2)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             out = run(K)

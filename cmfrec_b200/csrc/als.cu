@@ -1,6 +1,7 @@
 // See als.h.  Host-side orchestration only; all arithmetic on factor rows happens in the kernels.
 #include "als.h"
 #include "nccl_link.h"
+#include "device_prep.h"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -182,6 +183,117 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
+// processing order / bucket boundaries of a side whose ptr array is already on the device (single GPU, identity numbering)
+static int plan_side_from_device(DeviceSide &side, int_t rows, cudaStream_t stream)
+{
+    std::vector<size_t> hptr((size_t)rows + 1);
+    if (cudaMemcpyAsync(hptr.data(), side.ptr.p, hptr.size() * sizeof(size_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+        return 1;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+    side.rows_padded = rows;
+    side.block = rows;
+    side.row_begin = 0;
+    side.row_end = rows;
+    side.nnz_local = hptr[rows];
+    std::vector<int_t> order(rows);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int_t a, int_t b) {
+        return (hptr[a + 1] - hptr[a]) > (hptr[b + 1] - hptr[b]);
+    });
+    auto count_ge = [&](size_t thr, int_t limit) {
+        int_t c = 0;
+        while (c < limit && hptr[order[c] + 1] - hptr[order[c]] >= thr) c++;
+        return c;
+    };
+    side.n_order = rows;
+    side.n_long = count_ge((size_t)long_row_threshold(), rows);
+    side.n_huge = count_ge((size_t)env_or("CMFB200_HUGE_ROW", 8192), side.n_long);
+    side.n_big = count_ge((size_t)env_or("CMFB200_T_BIG", 512), rows);
+    side.n_mid = count_ge((size_t)env_or("CMFB200_T_MID", 96), rows);
+    if (!side.order.alloc(std::max<size_t>(order.size(), 1))) return 1;
+    if (rows) cudaMemcpyAsync(side.order.p, order.data(), order.size() * sizeof(int_t), cudaMemcpyHostToDevice, stream);
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+template <typename T> __global__ void scale_kernel(T *x, size_t n, T s)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = x[i] * s;
+}
+
+template <typename T> __global__ void write_bias_slot_kernel(T *F, int ld, int kk, const T *bias, int_t rows)
+{
+    const int_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) F[(size_t)r * ld + kk] = bias[r];
+}
+
+int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
+                             real_t scale, cudaStream_t s)
+{
+    cfg = c;
+    stream = s;
+    if (cfg.world != 1) return 2;
+    if (cfg.kk < 1 || cfg.kk > max_supported_k()) return 2;
+    if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    build_renumbering(nullptr, cfg.m, 1, renA);
+    build_renumbering(nullptr, cfg.n, 1, renB);
+    DevBuf<int_t> dA, dB;
+    DevBuf<real_t> dX;
+    const size_t cap = std::max<size_t>(nnz, 1);
+    if (!dA.alloc(cap) || !dB.alloc(cap) || !dX.alloc(cap)) return 1;
+    if (nnz) {
+        cudaMemcpyAsync(dA.p, ixA, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(dB.p, ixB, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(dX.p, X, nnz * sizeof(real_t), cudaMemcpyHostToDevice, stream);
+        if (mu != 0 && device_subtract(dX.p, nnz, mu, stream)) return 1;
+        if (scale != 1) scale_kernel<real_t><<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(dX.p, nnz, scale);
+    }
+    if (!byA.ptr.alloc((size_t)cfg.m + 1) || !byA.idx.alloc(cap) || !byA.val.alloc(cap) || !byB.ptr.alloc((size_t)cfg.n + 1) ||
+        !byB.idx.alloc(cap) || !byB.val.alloc(cap))
+        return 1;
+    int rc = device_compress(dA.p, dB.p, dX.p, nnz, cfg.m, byA.ptr.p, byA.idx.p, byA.val.p, stream);
+    if (rc) return rc;
+    rc = device_compress(dB.p, dA.p, dX.p, nnz, cfg.n, byB.ptr.p, byB.idx.p, byB.val.p, stream);
+    if (rc) return rc;
+    launches += 12;
+    if ((rc = plan_side_from_device(byA, cfg.m, stream))) return rc;
+    if ((rc = plan_side_from_device(byB, cfg.n, stream))) return rc;
+    ldA = cmf_ld_for(cfg.kk + 1);
+    ldB = cmf_ld_for(cfg.kk + 1);
+    if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB)) return 1;
+    cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream);
+    cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream);
+    if (cfg.implicit) {
+        if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
+    }
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+int AlsState::init_biases_on_device(int which, real_t lam_user, real_t lam_item, bool scale_lam)
+{
+    DevBuf<real_t> bA, bB;
+    if (!bA.alloc(std::max<int_t>(cfg.m, 1)) || !bB.alloc(std::max<int_t>(cfg.n, 1))) return 1;
+    int rc = 0;
+    const int threads = 256;
+    if (which == 3) {
+        rc = device_init_biases_twosided(cfg.m, cfg.n, byA.ptr.p, byA.idx.p, byA.val.p, byB.ptr.p, byB.idx.p, byB.val.p, lam_user,
+                                         lam_item, scale_lam, bA.p, bB.p, stream);
+        launches += 10;
+    } else if (which == 1) {
+        rc = device_init_biases_onesided(cfg.m, byA.ptr.p, byA.val.p, lam_user, scale_lam, bA.p, stream);
+        launches += 1;
+    } else if (which == 2) {
+        rc = device_init_biases_onesided(cfg.n, byB.ptr.p, byB.val.p, lam_item, scale_lam, bB.p, stream);
+        launches += 1;
+    }
+    if (rc) return rc;
+    if (which & 1) write_bias_slot_kernel<real_t><<<(cfg.m + threads - 1) / threads, threads, 0, stream>>>(A.p, ldA, cfg.kk, bA.p, cfg.m);
+    if (which & 2) write_bias_slot_kernel<real_t><<<(cfg.n + threads - 1) / threads, threads, 0, stream>>>(B.p, ldB, cfg.kk, bB.p, cfg.n);
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
 static void pack_factor(const real_t *h, int ldh, const real_t *hbias, int_t rows, int kk, const Renumbering &ren, int ld,
                         std::vector<real_t> &out)
 {
@@ -204,6 +316,31 @@ int AlsState::upload_factors(const real_t *hA, int lda, const real_t *hbiasA, co
     cudaStreamSynchronize(stream);
     pack_factor(hB, ldb, hbiasB, cfg.n, cfg.kk, renB, ldB, tmp);
     if (cudaMemcpyAsync(B.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+// bias slots of one side from a host array (identity numbering): which = 1 users, 2 items
+int AlsState::upload_bias(int which, const real_t *hbias)
+{
+    if (cfg.world != 1 || !hbias) return 2;
+    real_t *F = which == 1 ? A.p : B.p;
+    const int ld = which == 1 ? ldA : ldB;
+    const int_t rows = which == 1 ? cfg.m : cfg.n;
+    if (cudaMemcpy2DAsync(F + cfg.kk, (size_t)ld * sizeof(real_t), hbias, sizeof(real_t), sizeof(real_t), rows,
+                          cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+// factor coordinates only (bias slots and padding on the device are left untouched); identity numbering
+int AlsState::upload_coordinates(const real_t *hA, const real_t *hB)
+{
+    if (cfg.world != 1) return 2;
+    const size_t w = (size_t)cfg.kk * sizeof(real_t);
+    if (hA && cudaMemcpy2DAsync(A.p, (size_t)ldA * sizeof(real_t), hA, w, w, cfg.m, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return 1;
+    if (hB && cudaMemcpy2DAsync(B.p, (size_t)ldB * sizeof(real_t), hB, w, w, cfg.n, cudaMemcpyHostToDevice, stream) != cudaSuccess)
         return 1;
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }

@@ -89,8 +89,17 @@ public:
     // host CSR/CSC in caller numbering (values already centred / scaled as the model requires)
     int setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v, const size_t *csc_p,
               const int_t *csc_i, const real_t *csc_v, cudaStream_t s, const void *nccl_id);
+    // single-GPU ingestion straight from host COO triplets: upload, subtract `mu`, multiply by `scale`, build both
+    // orientations on the device (device_prep.cu).  Values are transformed as  (x - mu) * scale  in real_t.
+    int setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
+                       real_t scale, cudaStream_t s);
+    // starting biases computed on the device and written into the bias slots of A / B
+    // which: 3 = both sides (two-sided sweeps), 1 = users only, 2 = items only
+    int init_biases_on_device(int which, real_t lam_user, real_t lam_item, bool scale_lam);
     // factors in caller numbering: A [m x kk] (ld = lda), biasA [m] or null; same for B
     int upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb, const real_t *hbiasB);
+    int upload_coordinates(const real_t *hA, const real_t *hB);   // keeps the bias slots already on the device
+    int upload_bias(int which, const real_t *hbias);
     int download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB);
     // which: 0 = update B (items) from A, 1 = update A (users) from B.  `solver`: 0 = CG, 1 = Cholesky
     int half_sweep(int which, int iter, int solver);

@@ -1,0 +1,154 @@
+// Device-side ingestion for single-GPU fits: what the reference does on the host before the alternation starts,
+// done in HBM so that only the raw COO triplets cross PCIe.
+//
+//   COO -> CSR / CSC     reference coo_to_csr_and_csc, src/helpers.c:1375-1491: a STABLE counting sort (entries of a
+//                        row keep their COO order).  Here: stable LSD radix sort of (major index, position) pairs
+//                        (CUB DeviceRadixSort), then a gather; row pointers from a histogram + exclusive scan.
+//                        The integer outputs are identical to the reference's, entry for entry.
+//   centring             x - glob_mean in real_t                         src/common.c:3632-3644
+//   bias initialisation  initialize_biases_twosided / _onesided          src/common.c:4643-4669, 4799-4825, 4266-4289
+//                        one thread walks one row sequentially with the reference's operations in the reference's
+//                        order (running mean in double, residual formed in real_t), so results are bit-identical.
+#include "device_prep.h"
+#include <cub/cub.cuh>
+#include <cstdio>
+
+namespace cmfb200 {
+
+namespace {
+
+__global__ void iota_kernel(uint32_t *out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+__global__ void histogram_kernel(const int_t *__restrict__ major, size_t nnz, unsigned long long *__restrict__ counts)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) atomicAdd(&counts[major[i]], 1ULL);
+}
+
+template <typename T>
+__global__ void gather_kernel(const uint32_t *__restrict__ perm, const int_t *__restrict__ minor, const T *__restrict__ val,
+                              size_t nnz, int_t *__restrict__ out_idx, T *__restrict__ out_val)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) {
+        const uint32_t src = perm[i];
+        out_idx[i] = minor[src];
+        out_val[i] = val[src];
+    }
+}
+
+template <typename T> __global__ void subtract_kernel(T *x, size_t n, T mu)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = x[i] - mu;
+}
+
+// one sweep of the bias initialisation over one orientation: bias[r] = shrunken running mean of (x - other[idx])
+template <typename T>
+__global__ void bias_sweep_kernel(int_t rows, const size_t *__restrict__ ptr, const int_t *__restrict__ idx,
+                                  const T *__restrict__ val, const T *__restrict__ other, T lam, bool scale_lam,
+                                  bool clamp_count_to_one, bool shrink_empty, T *__restrict__ out)
+{
+    const int_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const size_t b = ptr[r], e = ptr[r + 1];
+    double mean = 0.;
+    // the running mean is a sequential chain, but the (gathered) residuals are not: fetch 8 at a time
+    size_t t = b;
+    for (; t + 8 <= e; t += 8) {
+        T resid[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) resid[u] = other ? (T)(val[t + u] - other[idx[t + u]]) : val[t + u];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid[u], mean), (double)(t + u - b + 1)));
+    }
+    for (; t < e; t++) {
+        const T resid = other ? (T)(val[t] - other[idx[t]]) : val[t];
+        mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid, mean), (double)(t - b + 1)));
+    }
+    const size_t cnt = e - b;
+    if (cnt > 0 || shrink_empty) {
+        const double c = (double)cnt;
+        const double mult = scale_lam ? (clamp_count_to_one ? (double)(cnt > 1 ? cnt : 1) : c) : 1.;
+        mean = __dmul_rn(mean, __ddiv_rn(c, __dadd_rn(c, __dmul_rn((double)lam, mult))));
+    }
+    out[r] = (T)mean;
+}
+
+}  // namespace
+
+int device_compress(const int_t *d_major, const int_t *d_minor, const real_t *d_val, size_t nnz, int_t nmajor,
+                    size_t *d_ptr, int_t *d_idx, real_t *d_out, cudaStream_t stream)
+{
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((nnz + threads - 1) / threads);
+    // row pointers
+    DevBuf<unsigned long long> counts;
+    if (!counts.alloc((size_t)nmajor + 1)) return 1;
+    cudaMemsetAsync(counts.p, 0, ((size_t)nmajor + 1) * sizeof(unsigned long long), stream);
+    if (nnz) histogram_kernel<<<blocks, threads, 0, stream>>>(d_major, nnz, counts.p);
+    size_t tb = 0;
+    static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, reinterpret_cast<unsigned long long *>(d_ptr), nmajor + 1, stream);
+    DevBuf<unsigned char> tmp;
+    if (!tmp.alloc(tb ? tb : 1)) return 1;
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, reinterpret_cast<unsigned long long *>(d_ptr), nmajor + 1, stream);
+    if (!nnz) return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+    // stable sort of positions by major index
+    DevBuf<uint32_t> pos_in, pos_out;
+    DevBuf<int_t> keys_out;
+    if (!pos_in.alloc(nnz) || !pos_out.alloc(nnz) || !keys_out.alloc(nnz)) return 1;
+    iota_kernel<<<blocks, threads, 0, stream>>>(pos_in.p, nnz);
+    int bits = 1;
+    while (bits < 31 && ((int_t)1 << bits) < nmajor) bits++;
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, d_major, keys_out.p, pos_in.p, pos_out.p, (int)nnz, 0, bits, stream);
+    DevBuf<unsigned char> stmp;
+    if (!stmp.alloc(sb ? sb : 1)) return 1;
+    cub::DeviceRadixSort::SortPairs(stmp.p, sb, d_major, keys_out.p, pos_in.p, pos_out.p, (int)nnz, 0, bits, stream);
+    gather_kernel<real_t><<<blocks, threads, 0, stream>>>(pos_out.p, d_minor, d_val, nnz, d_idx, d_out);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;   // temporaries are released on return
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int device_subtract(real_t *d_x, size_t n, real_t mu, cudaStream_t stream)
+{
+    if (!n) return 0;
+    subtract_kernel<real_t><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_x, n, mu);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int device_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
+                                const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, real_t lam_user, real_t lam_item,
+                                bool scale_lam, real_t *d_biasA, real_t *d_biasB, cudaStream_t stream)
+{
+    if (fabs((double)lam_user) < (double)CMF_EPS) lam_user = CMF_EPS;
+    if (fabs((double)lam_item) < (double)CMF_EPS) lam_item = CMF_EPS;
+    cudaMemsetAsync(d_biasA, 0, (size_t)m * sizeof(real_t), stream);
+    cudaMemsetAsync(d_biasB, 0, (size_t)n * sizeof(real_t), stream);
+    const int threads = 64;
+    for (int s = 0; s < 5; s++) {
+        bias_sweep_kernel<real_t><<<(n + threads - 1) / threads, threads, 0, stream>>>(n, csc_p, csc_i, csc_v, d_biasA, lam_item,
+                                                                                        scale_lam, true, true, d_biasB);
+        bias_sweep_kernel<real_t><<<(m + threads - 1) / threads, threads, 0, stream>>>(m, csr_p, csr_i, csr_v, d_biasB, lam_user,
+                                                                                        scale_lam, false, false, d_biasA);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int device_init_biases_onesided(int_t rows, const size_t *ptr, const real_t *val, real_t lam, bool scale_lam, real_t *d_bias,
+                                cudaStream_t stream)
+{
+    if (fabs((double)lam) < (double)CMF_EPS) lam = CMF_EPS;
+    const int threads = 64;
+    bias_sweep_kernel<real_t><<<(rows + threads - 1) / threads, threads, 0, stream>>>(rows, ptr, nullptr, val, nullptr, lam,
+                                                                                       scale_lam, true, true, d_bias);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace cmfb200

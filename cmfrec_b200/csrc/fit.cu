@@ -13,9 +13,34 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
+#include <chrono>
+#include <cstdlib>
+
 namespace cmfb200 {
+
+// CMFB200_TIMING=1 prints a wall-clock breakdown of a fit call to stderr
+struct StageTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0, born;
+    StageTimer() : on(std::getenv("CMFB200_TIMING") != nullptr), t0(std::chrono::steady_clock::now()), born(t0) {}
+    ~StageTimer()
+    {
+        if (on)
+            std::fprintf(stderr, "[cmfb200 timing] %-28s %8.2f ms\n", "total inside the call",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - born).count());
+    }
+    void lap(const char *what)
+    {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[cmfb200 timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static int refuse(const char *what)
 {
@@ -71,40 +96,22 @@ int fit_explicit(const ExplicitArgs &a)
         for (int i = 0; i < 6; i++) lam_u[i] /= a.w_main;
     }
 
-    // centring (src/collective.c:7555-7568 -> src/common.c:3423)
-    real_t glob_mean = 0;
-    std::vector<real_t> Xc(a.X, a.X + nnz);
-    if (a.center) {
-        glob_mean = global_mean(a.X, nnz, a.nthreads);
-        if (glob_mean != 0)
-            for (size_t e = 0; e < nnz; e++) Xc[e] -= glob_mean;
-    }
-    if (a.glob_mean) *a.glob_mean = glob_mean;
-
-    // both orientations of X (src/collective.c:7593 -> src/helpers.c:1375)
-    std::vector<size_t> csr_p((size_t)m + 1), csc_p((size_t)n + 1);
-    std::vector<int_t> csr_i(nnz), csc_i(nnz);
-    std::vector<real_t> csr_v(nnz), csc_v(nnz);
-    coo_to_csr_and_csc(a.ixA, a.ixB, Xc.data(), m, n, nnz, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(),
-                       csc_i.data(), csc_v.data());
-    std::vector<real_t>().swap(Xc);
-
-    // starting biases (src/collective.c:8164-8226)
-    if (has_bias) {
-        if (a.user_bias && a.item_bias) {
-            init_biases_twosided(m, n, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(), csc_i.data(), csc_v.data(),
-                                 lam_u[0], lam_u[1], scale_lam, false, a.biasA, a.biasB, a.nthreads);
-        } else if (a.user_bias) {
-            init_biases_onesided(m, csr_p.data(), csr_v.data(), lam_u[0], scale_lam, false, a.biasA);
-        } else if (use_cg) {
-            init_biases_onesided(n, csc_p.data(), csc_v.data(), lam_u[1], scale_lam, false, a.biasB);
-        }
-    }
-
-    // starting factors: A random, B zero with CG (src/collective.c:8241-8274)
+    StageTimer tm;
+    // starting factors on a host thread while the GPU ingests X: A random, B zero with CG
+    // (src/collective.c:8241-8274; reference helpers.c:930 semantics live in host_prep.cpp)
     const size_t sizeA = (size_t)m * kk, sizeB = (size_t)n * kk;
-    random_init(a.A, sizeA, nullptr, 0, a.seed, true);
-    if (use_cg) std::memset(a.B, 0, sizeB * sizeof(real_t));
+    std::thread rng([&]() {
+        random_init(a.A, sizeA, nullptr, 0, a.seed, true);
+        if (use_cg) std::memset(a.B, 0, sizeB * sizeof(real_t));
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
+
+    // centring (src/collective.c:7555-7568 -> src/common.c:3423): mean on the host (parity-critical summation
+    // order), subtraction on the device
+    real_t glob_mean = 0;
+    if (a.center) glob_mean = global_mean(a.X, nnz, a.nthreads);
+    if (a.glob_mean) *a.glob_mean = glob_mean;
+    tm.lap("global mean (host)");
 
     AlsConfig cfg;
     cfg.implicit = false;
@@ -117,17 +124,38 @@ int fit_explicit(const ExplicitArgs &a)
     cfg.max_cg_steps = a.max_cg_steps;
     (void)lam;
 
+    // upload COO, centre, build CSR + CSC on the device (src/collective.c:7593 -> src/helpers.c:1375)
     AlsState st;
-    int rc = st.setup(cfg, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(), csc_i.data(), csc_v.data(), nullptr,
-                      nullptr);
+    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, a.X, nnz, glob_mean, real_t(1), nullptr);
     if (rc) return rc == 2 ? refuse("this value of k") : rc;
-    rc = st.upload_factors(a.A, kk, a.user_bias ? a.biasA : nullptr, a.B, kk, a.item_bias ? a.biasB : nullptr);
+    tm.lap("upload COO + CSR/CSC (GPU)");
+
+    // starting biases (src/collective.c:8164-8226)
+    if (has_bias) {
+        int which = 0;
+        if (a.user_bias && a.item_bias) which = 3;
+        else if (a.user_bias) which = 1;
+        else if (use_cg) which = 2;
+        if (which && (rc = st.init_biases_on_device(which, lam_u[0], lam_u[1], scale_lam))) return rc;
+    }
+    tm.lap("bias initialisation (GPU)");
+
+    rng.join();
+    tm.lap("factor initialisation (host)");
+    // Cholesky-only fits never initialise B: pass the caller's buffer through like the reference does
+    rc = st.upload_coordinates(a.A, use_cg ? nullptr : a.B);
     if (rc) return rc;
+    if (a.item_bias && !a.user_bias && !use_cg) {
+        if ((rc = st.upload_bias(2, a.biasB))) return rc;   // left as the caller passed it (src/collective.c:8184)
+    }
+    tm.lap("upload factors");
     rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
     if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    tm.lap("ALS iterations");
     rc = st.download_factors(a.A, kk, a.user_bias ? a.biasA : nullptr, a.B, kk, a.item_bias ? a.biasB : nullptr);
     if (rc) return rc;
     if (cudaStreamSynchronize(nullptr) != cudaSuccess) return 1;
+    tm.lap("download factors");
 
     if (a.precompute_for_predictions) {
         PostfitExplicit pf;
@@ -160,23 +188,22 @@ int fit_implicit(const ImplicitArgs &a)
     bool use_cg = a.use_cg;
     const bool finalize_chol = a.finalize_chol && use_cg;
 
-    // value transform (src/collective.c:9578-9599)
-    std::vector<real_t> Xs(a.X, a.X + nnz);
-    if (a.apply_log_transf)
-        for (size_t e = 0; e < nnz; e++) Xs[e] = std::log(Xs[e]);
-    if (a.alpha != 1)
-        for (size_t e = 0; e < nnz; e++) Xs[e] *= a.alpha;
+    StageTimer tm;
+    // starting point on a host thread: A uniform (normal for tiny problems), B zero with CG (src/collective.c:9750-9774)
+    std::thread rng([&]() {
+        random_init(a.A, (size_t)m * kk, nullptr, 0, a.seed, false);
+        if (use_cg) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
 
-    std::vector<size_t> csr_p((size_t)m + 1), csc_p((size_t)n + 1);
-    std::vector<int_t> csr_i(nnz), csc_i(nnz);
-    std::vector<real_t> csr_v(nnz), csc_v(nnz);
-    coo_to_csr_and_csc(a.ixA, a.ixB, Xs.data(), m, n, nnz, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(),
-                       csc_i.data(), csc_v.data());
-    std::vector<real_t>().swap(Xs);
-
-    // starting point: A uniform (normal for tiny problems), B zero with CG (src/collective.c:9750-9774)
-    random_init(a.A, (size_t)m * kk, nullptr, 0, a.seed, false);
-    if (use_cg) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
+    // value transform (src/collective.c:9578-9599): log on the host (libm, as the reference), alpha on the device
+    std::vector<real_t> Xlog;
+    const real_t *Xsrc = a.X;
+    if (a.apply_log_transf) {
+        Xlog.assign(a.X, a.X + nnz);
+        for (size_t e = 0; e < nnz; e++) Xlog[e] = std::log(Xlog[e]);
+        Xsrc = Xlog.data();
+    }
 
     // weight bookkeeping (src/collective.c:9776-9811)
     real_t w_main = a.w_main;
@@ -198,15 +225,19 @@ int fit_implicit(const ImplicitArgs &a)
     cfg.max_cg_steps = a.max_cg_steps;
 
     AlsState st;
-    int rc = st.setup(cfg, csr_p.data(), csr_i.data(), csr_v.data(), csc_p.data(), csc_i.data(), csc_v.data(), nullptr,
-                      nullptr);
+    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, Xsrc, nnz, real_t(0), a.alpha, nullptr);
     if (rc) return rc == 2 ? refuse("this value of k") : rc;
-    rc = st.upload_factors(a.A, kk, nullptr, a.B, kk, nullptr);
+    tm.lap("upload COO + CSR/CSC (GPU)");
+    rng.join();
+    tm.lap("factor initialisation (host)");
+    rc = st.upload_coordinates(a.A, use_cg ? nullptr : a.B);
     if (rc) return rc;
     rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
     if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    tm.lap("ALS iterations");
     rc = st.download_factors(a.A, kk, nullptr, a.B, kk, nullptr);
     if (rc) return rc;
+    tm.lap("download factors");
 
     if (a.precompute_for_predictions && a.precomputedBtB) {
         // BtB + lam*I (src/collective.c:10057-10074)
