@@ -401,6 +401,10 @@ int AlsState::half_sweep(int which, int iter, int solver)
         // users: always when both biases are fitted; items: from the second iteration on
         // (src/collective.c:8538-8542, 8728-8732).
         p.bias_start_one = both && (solveA || iter > 0);
+        p.gram = extraQ[which ? 1 : 0];
+        p.qvec = extraq[which ? 1 : 0];
+        p.ldq = extra_ldq[which ? 1 : 0];
+        p.solve_all_rows = extra_all_rows[which ? 1 : 0];
     }
     int rc;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -418,7 +422,7 @@ int AlsState::half_sweep(int which, int iter, int solver)
     }
     if (solver == 0) {
         rc = 3;
-        if (env_or("CMFB200_STAGED", 0)) {
+        if (env_or("CMFB200_STAGED", 0) && (cfg.implicit || (!p.gram && !p.qvec && !p.solve_all_rows))) {
             rc = cfg.implicit ? launch_implicit_cg_sweep_staged(p, stream) : launch_explicit_cg_sweep_staged(p, stream);
             if (rc == 0) launches += 2;
         }

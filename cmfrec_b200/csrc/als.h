@@ -79,6 +79,12 @@ public:
     DevBuf<real_t> A, B;          // [rows_padded x ld], device numbering
     DevBuf<real_t> gram, gram_ws;
     NcclLink *link = nullptr;
+    // explicit model with side information / implicit features (collective.cu): constant matrix and per-row vector
+    // added to the systems of the rows of B ([0]) / of A ([1]); rows without entries are solved too when set
+    const real_t *extraQ[2] = {nullptr, nullptr};
+    const real_t *extraq[2] = {nullptr, nullptr};
+    int extra_ldq[2] = {0, 0};
+    bool extra_all_rows[2] = {false, false};
     long long launches = 0;       // kernels launched so far (for bench.py's gpu_launches)
     // optional per-launch timing of the row-solve kernel (CUDA events on `stream`, resolved on demand)
     bool profile = false;

@@ -51,7 +51,16 @@ template <typename T, int C, int L, int TW> struct TeamScratch {
 
 // CL > 1: the team spans the CL thread blocks of a cluster (TW warps in each); per-pass totals are then also
 // combined across the blocks through distributed shared memory (`cl_buf`, [2][KP+4] in every block).
-template <typename T, int C, int L, bool IMPLICIT, int TW, bool GRAM_SMEM, int CL = 1> struct CgRow {
+// MODEL: 0 = explicit feedback; 1 = implicit feedback (constant matrix = Gram of the opposing factor);
+//        2 = explicit feedback with side information / implicit features: a constant matrix Q (p.gram) is added to
+//            every row's system and a per-row vector q (p.qvec) to its right-hand side
+//            (reference collective_block_cg, src/collective.c:2134-2902: Q = w_user C^T C + w_implicit Bi^T Bi,
+//             q = w_user C^T u_i + w_implicit sum_e Bi_e).
+constexpr int kModelExplicit = 0, kModelImplicit = 1, kModelCollective = 2;
+
+template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 1> struct CgRow {
+    static constexpr bool IMPLICIT = MODEL == kModelImplicit;
+    static constexpr bool HAS_Q = MODEL != kModelExplicit;
     typedef Layout<T, C, L> Lay;
     typedef TeamScratch<T, C, L, TW> Scr;
     static constexpr int G = 32 / L;
@@ -185,7 +194,7 @@ template <typename T, int C, int L, bool IMPLICIT, int TW, bool GRAM_SMEM, int C
         if (hb) ab = p.bias_start_one ? T(1) : frow[kk];
 
         T lam = p.lam, lam_last = p.lam_last;
-        if (!IMPLICIT && p.scale_lam) {
+        if (!IMPLICIT && p.scale_lam && nnz > 0) {   // rows without entries (collective model only) keep lam as is
             lam *= (T)nnz;
             if (!p.scale_bias_const) lam_last *= (T)nnz;
         }
@@ -194,13 +203,16 @@ template <typename T, int C, int L, bool IMPLICIT, int TW, bool GRAM_SMEM, int C
 #pragma unroll
         for (int j = 0; j < C; j++) acc[j] = T(0);
         accb = T(0);
-        if constexpr (IMPLICIT) gram_matvec(a, T(-1), acc);
+        if constexpr (HAS_Q) gram_matvec(a, T(-1), acc);
         gather.template pass<IMPLICIT ? kImplicitResidual : kExplicitResidual>(a, ab, acc, accb);
         combine(acc, accb);
 #pragma unroll
         for (int j = 0; j < C; j++) {
             const int c = Lay::col(l, j);
             r[j] = (c < kk) ? fma(-lam, a[j], acc[j]) : T(0);
+            if constexpr (MODEL == kModelCollective) {
+                if (p.qvec && c < kk) r[j] += p.qvec[(size_t)row * (size_t)p.ldq + c];
+            }
         }
         if (hb) {
             rb = fma(-lam, ab, accb);
@@ -216,7 +228,7 @@ template <typename T, int C, int L, bool IMPLICIT, int TW, bool GRAM_SMEM, int C
 #pragma unroll
                 for (int j = 0; j < C; j++) acc[j] = T(0);
                 accb = T(0);
-                if constexpr (IMPLICIT) gram_matvec(pv, T(1), acc);
+                if constexpr (HAS_Q) gram_matvec(pv, T(1), acc);
                 gather.template pass<IMPLICIT ? kImplicitAp : kExplicitAp>(pv, pb, acc, accb);
                 combine(acc, accb);
 #pragma unroll
@@ -266,8 +278,22 @@ template <typename T, int C, int L, bool IMPLICIT, int TW, bool GRAM_SMEM, int C
     // bias column is the 1.0 written there before the sweep (src/collective.c:8538-8542)
     __device__ __forceinline__ void empty_row(int row) const
     {
-        if (!IMPLICIT && p.solve_bias && p.bias_start_one && lane == 0 && wt == 0)
-            p.F[(size_t)row * (size_t)p.ldF + p.kk] = T(1);
+        if constexpr (MODEL == kModelCollective) {
+            // reached only when the row has neither entries nor side information: the reference zeroes it
+            // (collective_closed_form_block "zero_out", src/collective.c:1259-1270)
+            if (g == 0 && wt == 0) {
+                T *frow = p.F + (size_t)row * (size_t)p.ldF;
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int c = Lay::col(l, j);
+                    if (c < p.kk) frow[c] = T(0);
+                }
+                if (l == 0 && p.solve_bias) frow[p.kk] = T(0);
+            }
+        } else {
+            if (!IMPLICIT && p.solve_bias && p.bias_start_one && lane == 0 && wt == 0)
+                p.F[(size_t)row * (size_t)p.ldF + p.kk] = T(1);
+        }
     }
 };
 

@@ -1,0 +1,285 @@
+// Small dense / sparse-dense building blocks of the models with side information and implicit features
+// (reference optimizeA Case 1 src/common.c:2793-2900, Case 3 :3117-3203; optimizeA_collective general case
+// src/collective.c:5566-5968).  None of these dominate an iteration; they are written for clarity and determinism.
+#include "dense_small.h"
+#include <cmath>
+#include <vector>
+
+namespace cmfb200 {
+
+namespace {
+
+constexpr int TILE = 64, PANEL = 16, MAX_SLICES = 64;
+
+// partial[slice][ncx][ncy] += X[rows of slice, :ncx]^T  Y[rows of slice, :ncy]   (64x64 tiles, 4x4 per thread)
+template <typename T>
+__global__ void __launch_bounds__(256) xty_partial_kernel(const T *__restrict__ X, int ldx, int ncx, const T *__restrict__ Y,
+                                                          int ldy, int ncy, int_t rows, int nslices, T *__restrict__ partial)
+{
+    __shared__ T sa[PANEL][TILE + 1];
+    __shared__ T sb[PANEL][TILE + 1];
+    const int ti = blockIdx.x, tj = blockIdx.y, slice = blockIdx.z;
+    const long long per = ((long long)rows + nslices - 1) / nslices;
+    const long long r_begin = (long long)slice * per;
+    long long r_end = r_begin + per;
+    if (r_end > rows) r_end = rows;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = T(0);
+    for (long long r0 = r_begin; r0 < r_end; r0 += PANEL) {
+        for (int i = threadIdx.x; i < PANEL * TILE; i += 256) {
+            const int rr = i / TILE, cc = i % TILE;
+            const long long r = r0 + rr;
+            const int ca = ti * TILE + cc, cb = tj * TILE + cc;
+            const bool ok = r < r_end;
+            sa[rr][cc] = (ok && ca < ncx) ? X[(size_t)r * ldx + ca] : T(0);
+            sb[rr][cc] = (ok && cb < ncy) ? Y[(size_t)r * ldy + cb] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < PANEL; rr++) {
+            T av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) av[i] = sa[rr][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bv[j] = sb[rr][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    T *out = partial + (size_t)slice * ncx * ncy;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int a = ti * TILE + ty + 16 * i, b = tj * TILE + tx + 16 * j;
+            if (a < ncx && b < ncy) out[(size_t)a * ncy + b] = acc[i][j];
+        }
+}
+
+template <typename T> __global__ void sum_slices_kernel(const T *__restrict__ partial, int total, int nslices, T *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    T s = T(0);
+    for (int sl = 0; sl < nslices; sl++) s += partial[(size_t)sl * total + i];
+    out[i] = s;
+}
+
+// out[r, :nc] = alpha * M[r, :p] . S[:p, :nc]  (+ out if accumulate); one warp per row, S cached in shared memory
+template <typename T>
+__global__ void rows_times_small_kernel(const T *__restrict__ M, int ldm, int p, const T *__restrict__ S, int lds, int nc,
+                                        T alpha, bool accumulate, T *__restrict__ out, int ldo, int_t rows)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Ss = reinterpret_cast<T *>(smem_raw);
+    for (int i = threadIdx.x; i < p * nc; i += blockDim.x) Ss[i] = S[(size_t)(i / nc) * lds + (i % nc)];
+    __syncthreads();
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int_t r = blockIdx.x * warps + w; r < rows; r += gridDim.x * warps) {
+        const T *mrow = M + (size_t)r * ldm;
+        for (int c = lane; c < nc; c += 32) {
+            T s = T(0);
+            for (int q = 0; q < p; q++) s = fma(mrow[q], Ss[q * nc + c], s);
+            T *o = out + (size_t)r * ldo + c;
+            *o = accumulate ? fma(alpha, s, *o) : alpha * s;
+        }
+    }
+}
+
+// Y[r, :kk] = alpha * sum_{e in row r} F[idx_e, :kk]  (+ Y if accumulate); warp per row, block per long row
+template <typename T>
+__global__ void __launch_bounds__(256) spmm_ones_kernel(const size_t *__restrict__ ptr, const int_t *__restrict__ idx,
+                                                        const int_t *__restrict__ order, int_t n_rows, int_t n_long,
+                                                        const T *__restrict__ F, int ldf, int kk, T alpha, bool accumulate,
+                                                        T *__restrict__ Y, int ldy)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *red = reinterpret_cast<T *>(smem_raw);   // [8][kk]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slots = n_long + (n_rows - n_long + 7) / 8;
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        const bool team = slot < n_long;
+        const int i = team ? slot : n_long + (slot - n_long) * 8 + w;
+        if (i >= n_rows) continue;   // warp-uniform; team slots never take this branch
+        const int_t row = order[i];
+        const size_t b = ptr[row], e = ptr[row + 1];
+        for (int c0 = 0; c0 < kk; c0 += 32) {
+            const int c = c0 + lane;
+            T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+            size_t t = b + (team ? w : 0);
+            const size_t step = team ? 8 : 1;
+            if (c < kk) {
+                for (; t + 3 * step < e; t += 4 * step) {
+                    s0 += F[(size_t)idx[t] * ldf + c];
+                    s1 += F[(size_t)idx[t + step] * ldf + c];
+                    s2 += F[(size_t)idx[t + 2 * step] * ldf + c];
+                    s3 += F[(size_t)idx[t + 3 * step] * ldf + c];
+                }
+                for (; t < e; t += step) s0 += F[(size_t)idx[t] * ldf + c];
+            }
+            T s = (s0 + s1) + (s2 + s3);
+            if (team) {
+                __syncthreads();
+                if (c < kk) red[w * kk + c] = s;
+                __syncthreads();
+                if (w == 0 && c < kk) {
+                    s = T(0);
+                    for (int ww = 0; ww < 8; ww++) s += red[ww * kk + c];
+                }
+            }
+            if ((!team || w == 0) && c < kk) {
+                T *o = Y + (size_t)row * ldy + c;
+                *o = accumulate ? fma(alpha, s, *o) : alpha * s;
+            }
+        }
+        if (team) __syncthreads();
+    }
+}
+
+// R[r, :d] := solution of (L L^T) x = R[r, :d]; L lower-triangular [d x d] row-major; one warp per row
+template <typename T>
+__global__ void tri_solve_rows_kernel(const T *__restrict__ Lmat, int d, T *__restrict__ R, int ldr, int_t rows)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Ls = reinterpret_cast<T *>(smem_raw);                  // [d][d+1]
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *ys = Ls + (size_t)d * (d + 1) + (size_t)w * d;         // [warps][d]
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) Ls[(i / d) * (d + 1) + (i % d)] = Lmat[i];
+    __syncthreads();
+    for (int_t r = blockIdx.x * warps + w; r < rows; r += gridDim.x * warps) {
+        T *x = R + (size_t)r * ldr;
+        for (int i = lane; i < d; i += 32) ys[i] = x[i];
+        __syncwarp();
+        for (int i = 0; i < d; i++) {                         // forward: L y = b
+            T s = T(0);
+            for (int t = lane; t < i; t += 32) s = fma(Ls[i * (d + 1) + t], ys[t], s);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) ys[i] = (ys[i] - s) / Ls[i * (d + 1) + i];
+            __syncwarp();
+        }
+        for (int i = d - 1; i >= 0; i--) {                    // backward: L^T x = y
+            T s = T(0);
+            for (int t = i + 1 + lane; t < d; t += 32) s = fma(Ls[t * (d + 1) + i], ys[t], s);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) ys[i] = (ys[i] - s) / Ls[i * (d + 1) + i];
+            __syncwarp();
+        }
+        for (int i = lane; i < d; i += 32) x[i] = ys[i];
+        __syncwarp();
+    }
+}
+
+template <typename T> __global__ void axpby_kernel(int n, T alpha, const T *x, T beta, const T *y, T *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (x ? alpha * x[i] : T(0)) + (y ? beta * y[i] : T(0));
+}
+
+int sm_count()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+}  // namespace
+
+size_t xty_workspace_elems(int ncx, int ncy) { return (size_t)MAX_SLICES * ncx * ncy; }
+
+int launch_xty(const real_t *X, int ldx, int ncx, const real_t *Y, int ldy, int ncy, int_t rows, real_t *out, real_t *workspace,
+               cudaStream_t stream)
+{
+    if (ncx < 1 || ncy < 1) return 2;
+    const int tx = (ncx + TILE - 1) / TILE, ty = (ncy + TILE - 1) / TILE;
+    int ns = (2 * sm_count() + tx * ty - 1) / (tx * ty);
+    if (ns > MAX_SLICES) ns = MAX_SLICES;
+    const long long by_rows = ((long long)rows + 4 * PANEL - 1) / (4 * PANEL);
+    if (ns > by_rows) ns = (int)by_rows;
+    if (ns < 1) ns = 1;
+    xty_partial_kernel<real_t><<<dim3(tx, ty, ns), 256, 0, stream>>>(X, ldx, ncx, Y, ldy, ncy, rows, ns, workspace);
+    const int total = ncx * ncy;
+    sum_slices_kernel<real_t><<<(total + 255) / 256, 256, 0, stream>>>(workspace, total, ns, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_rows_times_small(const real_t *M, int ldm, int p, const real_t *S, int lds, int nc, real_t alpha, bool accumulate,
+                            real_t *out, int ldo, int_t rows, cudaStream_t stream)
+{
+    if (rows < 1 || p < 1) return 0;
+    const size_t smem = (size_t)p * nc * sizeof(real_t);
+    auto kern = rows_times_small_kernel<real_t>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 2;
+    }
+    int blocks = (int)std::min<long long>(((long long)rows + 7) / 8, 4LL * sm_count());
+    kern<<<blocks, 256, smem, stream>>>(M, ldm, p, S, lds, nc, alpha, accumulate, out, ldo, rows);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_spmm_ones(const CsrView &X, const SweepPlan &plan, const real_t *F, int ldf, int kk, real_t alpha, bool accumulate,
+                     real_t *Y, int ldy, cudaStream_t stream)
+{
+    if (plan.n_rows < 1) return 0;
+    const int n_slots = plan.n_long + (plan.n_rows - plan.n_long + 7) / 8;
+    int blocks = std::min(n_slots, 8 * sm_count());
+    spmm_ones_kernel<real_t><<<blocks, 256, (size_t)8 * kk * sizeof(real_t), stream>>>(X.ptr, X.idx, plan.order, plan.n_rows,
+                                                                                        plan.n_long, F, ldf, kk, alpha,
+                                                                                        accumulate, Y, ldy);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int spd_factor_host(int d, const real_t *S_host, std::vector<real_t> &L_host)
+{
+    std::vector<double> Lm((size_t)d * d, 0.);
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j <= i; j++) Lm[(size_t)i * d + j] = S_host[(size_t)i * d + j];
+    for (int j = 0; j < d; j++) {
+        double s = Lm[(size_t)j * d + j];
+        for (int t = 0; t < j; t++) s -= Lm[(size_t)j * d + t] * Lm[(size_t)j * d + t];
+        if (!(s > 0)) return 1;
+        const double dj = std::sqrt(s);
+        Lm[(size_t)j * d + j] = dj;
+        for (int i = j + 1; i < d; i++) {
+            double v = Lm[(size_t)i * d + j];
+            for (int t = 0; t < j; t++) v -= Lm[(size_t)i * d + t] * Lm[(size_t)j * d + t];
+            Lm[(size_t)i * d + j] = v / dj;
+        }
+    }
+    L_host.resize((size_t)d * d);
+    for (size_t i = 0; i < L_host.size(); i++) L_host[i] = (real_t)Lm[i];
+    return 0;
+}
+
+int launch_tri_solve_rows(const real_t *L_dev, int d, real_t *R, int ldr, int_t rows, cudaStream_t stream)
+{
+    if (rows < 1) return 0;
+    const int warps = 8;
+    const size_t smem = ((size_t)d * (d + 1) + (size_t)warps * d) * sizeof(real_t);
+    auto kern = tri_solve_rows_kernel<real_t>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 2;
+    }
+    int blocks = (int)std::min<long long>(((long long)rows + warps - 1) / warps, 4LL * sm_count());
+    kern<<<blocks, warps * 32, smem, stream>>>(L_dev, d, R, ldr, rows);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_axpby(int n, real_t alpha, const real_t *x, real_t beta, const real_t *y, real_t *out, cudaStream_t stream)
+{
+    axpby_kernel<real_t><<<(n + 255) / 256, 256, 0, stream>>>(n, alpha, x, beta, y, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace cmfb200

@@ -10,6 +10,7 @@
 #include "als.h"
 #include "host_prep.h"
 #include "postfit.h"
+#include "collective.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -66,14 +67,23 @@ int fit_explicit(const ExplicitArgs &a)
     if (a.Xfull) return refuse("dense X (Xfull)");
     if (a.weight) return refuse("observation weights");
     if (a.NA_as_zero_X) return refuse("NA_as_zero_X");
-    if (a.U || a.II || a.nnz_U || a.nnz_I) return refuse("side information (U / I)");
-    if (a.add_implicit_features) return refuse("add_implicit_features");
+    if (a.nnz_U || a.nnz_I) return refuse("sparse side information (U_sp / I_sp)");
+    if (a.NA_as_zero_U || a.NA_as_zero_I) return refuse("NA_as_zero_U / NA_as_zero_I");
+    if (a.U && a.m_u != a.m) return refuse("side information U with a different number of rows than X");
+    if (a.II && a.n_i != a.n) return refuse("side information I with a different number of rows than X has columns");
     if (a.nonneg || a.nonneg_C || a.nonneg_D) return refuse("non-negativity constraints");
     if (a.l1_lam != 0 || a.l1_lam_unique) return refuse("L1 regularisation");
     if (a.precondition_cg) return refuse("precondition_cg");
-    if (a.k_user || a.k_item) return refuse("k_user / k_item without side information");
+    if (a.k_user || a.k_item) return refuse("k_user / k_item");
+    if (a.scale_lam_sideinfo) return refuse("scale_lam_sideinfo");
     if (a.scale_bias_const && (a.scale_lam || a.scale_lam_sideinfo) && (a.user_bias || a.item_bias))
         return refuse("scale_bias_const");
+    const bool collective = a.U || a.II || a.add_implicit_features;
+    if (collective && a.k_main) return refuse("k_main together with side information / implicit features");
+    if (collective && a.precompute_for_predictions)
+        return refuse("precompute_for_predictions together with side information / implicit features");
+    if (a.add_implicit_features && (!a.Ai || !a.Bi)) return 2;
+    if ((a.U && !a.C) || (a.II && !a.D)) return 2;
     if (!a.reset_values) return refuse("reset_values = false");
     if (a.m < 1 || a.n < 1 || a.k + a.k_main < 1) return 2;
     if (int rc = cuda_ready()) return rc;
@@ -100,9 +110,10 @@ int fit_explicit(const ExplicitArgs &a)
     // starting factors on a host thread while the GPU ingests X: A random, B zero with CG
     // (src/collective.c:8241-8274; reference helpers.c:930 semantics live in host_prep.cpp)
     const size_t sizeA = (size_t)m * kk, sizeB = (size_t)n * kk;
+    const bool fill_B = a.II || a.add_implicit_features;   // src/collective.c:8243
     std::thread rng([&]() {
-        random_init(a.A, sizeA, nullptr, 0, a.seed, true);
-        if (use_cg) std::memset(a.B, 0, sizeB * sizeof(real_t));
+        random_init(a.A, sizeA, fill_B ? a.B : nullptr, fill_B ? sizeB : 0, a.seed, true);
+        if (use_cg && !fill_B) std::memset(a.B, 0, sizeB * sizeof(real_t));
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
 
@@ -143,14 +154,45 @@ int fit_explicit(const ExplicitArgs &a)
     rng.join();
     tm.lap("factor initialisation (host)");
     // Cholesky-only fits never initialise B: pass the caller's buffer through like the reference does
-    rc = st.upload_coordinates(a.A, use_cg ? nullptr : a.B);
+    rc = st.upload_coordinates(a.A, (use_cg && !fill_B) ? nullptr : a.B);
     if (rc) return rc;
     if (a.item_bias && !a.user_bias && !use_cg) {
         if ((rc = st.upload_bias(2, a.biasB))) return rc;   // left as the caller passed it (src/collective.c:8184)
     }
     tm.lap("upload factors");
-    rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
-    if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    if (!collective) {
+        rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
+        if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    } else {
+        // side information: column-centre (U_colmeans / I_colmeans are outputs), then the C, D, Bi, Ai, B, A loop
+        real_t w_user = a.w_user, w_item = a.w_item, w_imp = a.w_implicit;
+        if (a.w_main != 1) { w_user /= a.w_main; w_item /= a.w_main; w_imp /= a.w_main; }
+        std::vector<real_t> Uc, Ic;
+        CollectiveConfig cc;
+        if (a.U) {
+            cc.p = a.p;
+            if (a.U_colmeans) { if (center_side_info(a.U, m, a.p, a.U_colmeans, Uc)) return refuse("missing values in U"); }
+            else Uc.assign(a.U, a.U + (size_t)m * a.p);
+        }
+        if (a.II) {
+            cc.q = a.q;
+            if (a.I_colmeans) { if (center_side_info(a.II, n, a.q, a.I_colmeans, Ic)) return refuse("missing values in I"); }
+            else Ic.assign(a.II, a.II + (size_t)n * a.q);
+        }
+        for (real_t v : Uc) if (std::isnan(v)) return refuse("missing values in U");
+        for (real_t v : Ic) if (std::isnan(v)) return refuse("missing values in I");
+        cc.implicit_features = a.add_implicit_features;
+        cc.w_user = w_user; cc.w_item = w_item; cc.w_implicit = w_imp;
+        cc.lam_C = lam_u[4] / w_user * (scale_lam ? (real_t)m : real_t(1));
+        cc.lam_D = lam_u[5] / w_item * (scale_lam ? (real_t)n : real_t(1));
+        cc.lam_Bi = lam_u[3] / w_imp * (scale_lam ? (real_t)m : real_t(1));
+        cc.lam_Ai = lam_u[2] / w_imp * (scale_lam ? (real_t)n : real_t(1));
+        CollectiveState cs;
+        if ((rc = cs.setup(&st, cc, Uc.data(), Ic.data()))) return rc;
+        rc = cs.iterate(a.niter, use_cg, finalize_chol);
+        if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+        if ((rc = cs.download(a.C, a.D, a.Ai, a.Bi))) return rc;
+    }
     tm.lap("ALS iterations");
     rc = st.download_factors(a.A, kk, a.user_bias ? a.biasA : nullptr, a.B, kk, a.item_bias ? a.biasB : nullptr);
     if (rc) return rc;

@@ -37,7 +37,10 @@ struct CgSweepParams {
     bool center_opp;              // subtract the opposing row's bias slot from every x before use
     bool bias_start_one;          // start the bias coordinate from 1.0 instead of the stored bias
     int max_cg_steps;
-    const real_t *gram;           // implicit only: G^T G, [kk x kk] row-major, full symmetric
+    const real_t *gram;           // constant [kk x kk] matrix (row-major, full symmetric) added to every row's system:
+                                  // implicit model: G^T G; explicit model with side info / implicit features: Q
+    const real_t *qvec; int ldq;  // explicit + side info: per-row vector [rows x ldq] added to the right-hand side
+    bool solve_all_rows;          // explicit + side info: rows without stored entries are solved too
     cudaStream_t side_stream;     // optional second stream for the long-row kernel (caller orders it around the sweep)
 };
 

@@ -112,7 +112,7 @@ template <typename T, int C, int L, int TW> struct DirectGather {
     }
 };
 
-template <typename T, int C, int L, bool IMPLICIT, bool GRAM_SMEM>
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgSweepParams p)
 {
     typedef Layout<T, C, L> Lay;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgS
     T *scratch_warp = scratch_team + TeamScratch<T, C, L, W>::elems();         // [W] warp-per-row scratch
     T *gram_sm = scratch_warp + W * TeamScratch<T, C, L, 1>::elems();          // [kk][KP] (implicit, if it fits)
     const T *gram = p.gram;
-    if constexpr (IMPLICIT && GRAM_SMEM) {
+    if constexpr (MODEL != kModelExplicit && GRAM_SMEM) {
         const int kk = p.kk;
         for (int i = threadIdx.x; i < kk * Lay::KP; i += blockDim.x) {
             const int d = i / Lay::KP, c = i % Lay::KP;
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgS
             const int row = p.plan.order[slot];
             const size_t beg = p.X.ptr[row];
             const int nnz = (int)(p.X.ptr[row + 1] - beg);
-            CgRow<T, C, L, IMPLICIT, W, GRAM_SMEM> s(p, scratch_team, gram, w, 0);
-            if (nnz > 0) {
+            CgRow<T, C, L, MODEL, W, GRAM_SMEM> s(p, scratch_team, gram, w, 0);
+            if (nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows)) {
                 DirectGather<T, C, L, W> gat(p, w);
                 gat.beg = beg; gat.nnz = nnz;
                 s.solve(row, nnz, gat);
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgS
                 const int row = p.plan.order[i];
                 const size_t beg = p.X.ptr[row];
                 const int nnz = (int)(p.X.ptr[row + 1] - beg);
-                CgRow<T, C, L, IMPLICIT, 1, GRAM_SMEM> s(p, scratch_warp + w * TeamScratch<T, C, L, 1>::elems(), gram, 0, 0);
-                if (nnz > 0) {
+                CgRow<T, C, L, MODEL, 1, GRAM_SMEM> s(p, scratch_warp + w * TeamScratch<T, C, L, 1>::elems(), gram, 0, 0);
+                if (nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows)) {
                     DirectGather<T, C, L, 1> gat(p, 0);
                     gat.beg = beg; gat.nnz = nnz;
                     s.solve(row, nnz, gat);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgS
 // cluster; the per-pass sums are combined through distributed shared memory (cg_row.cuh, CL > 1).
 constexpr int kClusterSize = 8;
 
-template <typename T, int C, int L, bool IMPLICIT>
+template <typename T, int C, int L, int MODEL>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kWarpsPerBlock * 32)
     cg_sweep_cluster_kernel(const CgSweepParams p, int n_huge)
 {
@@ -192,7 +192,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kWarpsPer
         const int row = p.plan.order[slot];
         const size_t beg = p.X.ptr[row];
         const int nnz = (int)(p.X.ptr[row + 1] - beg);
-        CgRow<T, C, L, IMPLICIT, W, false, kClusterSize> s(p, scratch, p.gram, w, 0);
+        CgRow<T, C, L, MODEL, W, false, kClusterSize> s(p, scratch, p.gram, w, 0);
         s.cl_buf = cl_buf;
         DirectGather<T, C, L, W> gat(p, w);
         gat.beg = beg; gat.nnz = nnz;
@@ -204,7 +204,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kWarpsPer
     }
 }
 
-template <typename T, int C, int L, bool IMPLICIT>
+template <typename T, int C, int L, int MODEL>
 int launch_cluster_cfg(const CgSweepParams &p, int n_huge, cudaStream_t stream)
 {
     if (n_huge <= 0) return 0;
@@ -217,20 +217,20 @@ int launch_cluster_cfg(const CgSweepParams &p, int n_huge, cudaStream_t stream)
     int clusters = n_huge;
     const int max_clusters = 2 * (sms / kClusterSize);
     if (clusters > max_clusters) clusters = max_clusters;
-    auto kern = cg_sweep_cluster_kernel<T, C, L, IMPLICIT>;
+    auto kern = cg_sweep_cluster_kernel<T, C, L, MODEL>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<clusters * kClusterSize, W * 32, smem, stream>>>(p, n_huge);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-template <typename T, int C, int L, bool IMPLICIT>
+template <typename T, int C, int L, int MODEL>
 int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
 {
     // the first n_huge rows of the (degree-sorted) order go to the cluster kernel, the rest to the main kernel
     CgSweepParams p = p_in;
     int n_huge = p.plan.n_huge < p.plan.n_long ? p.plan.n_huge : p.plan.n_long;
     if (n_huge > 0) {
-        int rc = launch_cluster_cfg<T, C, L, IMPLICIT>(p_in, n_huge, p_in.side_stream ? p_in.side_stream : stream);
+        int rc = launch_cluster_cfg<T, C, L, MODEL>(p_in, n_huge, p_in.side_stream ? p_in.side_stream : stream);
         if (rc) return rc;
         p.plan.order += n_huge;
         p.plan.n_rows -= n_huge;
@@ -239,8 +239,8 @@ int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
     typedef Layout<T, C, L> Lay;
     constexpr int W = kWarpsPerBlock;
     size_t smem = (size_t)(TeamScratch<T, C, L, W>::elems() + W * TeamScratch<T, C, L, 1>::elems()) * sizeof(T);
-    const size_t gram_bytes = IMPLICIT ? (size_t)p.kk * Lay::KP * sizeof(T) : 0;
-    const bool gram_in_smem = IMPLICIT && (smem + gram_bytes <= 100 * 1024);
+    const size_t gram_bytes = MODEL != kModelExplicit ? (size_t)p.kk * Lay::KP * sizeof(T) : 0;
+    const bool gram_in_smem = MODEL != kModelExplicit && (smem + gram_bytes <= 100 * 1024);
     if (gram_in_smem) smem += gram_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -248,7 +248,7 @@ int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
     const int n_long = p.plan.n_long;
     const int n_slots = n_long + (p.plan.n_rows - n_long + W - 1) / W;
     if (n_slots <= 0) return 0;
-    auto kern = gram_in_smem ? cg_sweep_kernel<T, C, L, IMPLICIT, true> : cg_sweep_kernel<T, C, L, IMPLICIT, false>;
+    auto kern = gram_in_smem ? cg_sweep_kernel<T, C, L, MODEL, true> : cg_sweep_kernel<T, C, L, MODEL, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem);
@@ -264,30 +264,30 @@ int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-template <bool IMPLICIT> int dispatch(const CgSweepParams &p, cudaStream_t stream)
+template <int MODEL> int dispatch(const CgSweepParams &p, cudaStream_t stream)
 {
     const int kk = p.kk;
     if (kk < 1) return 2;
 #ifdef USE_FLOAT
-    if (kk <= 16) return launch_cfg<float, 4, 4, IMPLICIT>(p, stream);
-    if (kk <= 32) return launch_cfg<float, 8, 4, IMPLICIT>(p, stream);
+    if (kk <= 16) return launch_cfg<float, 4, 4, MODEL>(p, stream);
+    if (kk <= 32) return launch_cfg<float, 8, 4, MODEL>(p, stream);
     if (kk <= 64) {
         const char *e = std::getenv("CMFB200_CFG64");
         const int v = e ? std::atoi(e) : 0;
-        if (v == 1) return launch_cfg<float, 8, 8, IMPLICIT>(p, stream);
-        if (v == 2) return launch_cfg<float, 4, 16, IMPLICIT>(p, stream);
-        return launch_cfg<float, 16, 4, IMPLICIT>(p, stream);   // measured fastest: 8 entries in flight per warp
+        if (v == 1) return launch_cfg<float, 8, 8, MODEL>(p, stream);
+        if (v == 2) return launch_cfg<float, 4, 16, MODEL>(p, stream);
+        return launch_cfg<float, 16, 4, MODEL>(p, stream);   // measured fastest: 8 entries in flight per warp
     }
-    if (kk <= 128) return launch_cfg<float, 8, 16, IMPLICIT>(p, stream);
-    if (kk <= 256) return launch_cfg<float, 8, 32, IMPLICIT>(p, stream);
-    if (kk <= 512) return launch_cfg<float, 16, 32, IMPLICIT>(p, stream);
+    if (kk <= 128) return launch_cfg<float, 8, 16, MODEL>(p, stream);
+    if (kk <= 256) return launch_cfg<float, 8, 32, MODEL>(p, stream);
+    if (kk <= 512) return launch_cfg<float, 16, 32, MODEL>(p, stream);
 #else
-    if (kk <= 16) return launch_cfg<double, 4, 4, IMPLICIT>(p, stream);
-    if (kk <= 32) return launch_cfg<double, 4, 8, IMPLICIT>(p, stream);
-    if (kk <= 64) return launch_cfg<double, 4, 16, IMPLICIT>(p, stream);
-    if (kk <= 128) return launch_cfg<double, 4, 32, IMPLICIT>(p, stream);
-    if (kk <= 256) return launch_cfg<double, 8, 32, IMPLICIT>(p, stream);
-    if (kk <= 512) return launch_cfg<double, 16, 32, IMPLICIT>(p, stream);
+    if (kk <= 16) return launch_cfg<double, 4, 4, MODEL>(p, stream);
+    if (kk <= 32) return launch_cfg<double, 4, 8, MODEL>(p, stream);
+    if (kk <= 64) return launch_cfg<double, 4, 16, MODEL>(p, stream);
+    if (kk <= 128) return launch_cfg<double, 4, 32, MODEL>(p, stream);
+    if (kk <= 256) return launch_cfg<double, 8, 32, MODEL>(p, stream);
+    if (kk <= 512) return launch_cfg<double, 16, 32, MODEL>(p, stream);
 #endif
     return 2;
 }
@@ -296,7 +296,10 @@ template <bool IMPLICIT> int dispatch(const CgSweepParams &p, cudaStream_t strea
 
 int max_supported_k() { return 512; }
 
-int launch_explicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch<false>(p, stream); }
-int launch_implicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch<true>(p, stream); }
+int launch_explicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream)
+{
+    return (p.gram || p.qvec || p.solve_all_rows) ? dispatch<kModelCollective>(p, stream) : dispatch<kModelExplicit>(p, stream);
+}
+int launch_implicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch<kModelImplicit>(p, stream); }
 
 }  // namespace cmfb200

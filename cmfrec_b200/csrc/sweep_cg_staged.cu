@@ -300,7 +300,7 @@ template <typename T, int C, int L, int TW, int WPB> struct StagedSmem {
     }
 };
 
-template <typename T, int C, int L, bool IMPLICIT, int TW, int WPB, bool GRAM_SMEM>
+template <typename T, int C, int L, int MODEL, int TW, int WPB, bool GRAM_SMEM>
 __global__ void __launch_bounds__(WPB * 32) cg_sweep_staged_kernel(const CgSweepParams p, int first, int count, int NS, int RS)
 {
     typedef Layout<T, C, L> Lay;
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(WPB * 32) cg_sweep_staged_kernel(const CgSweep
 
     size_t gram_bytes = 0;
     const T *gram = p.gram;
+    constexpr bool IMPLICIT = MODEL == kModelImplicit;
     if constexpr (IMPLICIT && GRAM_SMEM) {
         T *gram_sm = reinterpret_cast<T *>(smem_raw);
         const int kk = p.kk;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(WPB * 32) cg_sweep_staged_kernel(const CgSweep
     }
     __syncthreads();
 
-    CgRow<T, C, L, IMPLICIT, TW, GRAM_SMEM> solver(p, scratch, gram, wt, 1 + team);
+    CgRow<T, C, L, MODEL, TW, GRAM_SMEM> solver(p, scratch, gram, wt, 1 + team);
     Gat gat(p, rows, xs, full, empty, NS, RS, wt);
     const int team_global = blockIdx.x * SM::TEAMS + team;
     const int total_teams = gridDim.x * SM::TEAMS;
@@ -403,8 +404,8 @@ int launch_bucket(const CgSweepParams &p, int first, int count, int blocks_per_s
     while (NS < 32 && gram_bytes + (size_t)SM::TEAMS * SM::team_bytes(NS + 1, RS) <= budget) NS++;
     if (NS < 2) return 3;   // does not fit: caller falls back to the direct-gather kernel
     const size_t smem = gram_bytes + (size_t)SM::TEAMS * SM::team_bytes(NS, RS);
-    auto kern = gram_smem ? cg_sweep_staged_kernel<T, C, L, IMPLICIT, TW, WPB, true>
-                          : cg_sweep_staged_kernel<T, C, L, IMPLICIT, TW, WPB, false>;
+    auto kern = gram_smem ? cg_sweep_staged_kernel<T, C, L, IMPLICIT ? kModelImplicit : kModelExplicit, TW, WPB, true>
+                          : cg_sweep_staged_kernel<T, C, L, IMPLICIT ? kModelImplicit : kModelExplicit, TW, WPB, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 3;

@@ -12,8 +12,7 @@
 // the 256 threads of the block (each stored entry is staged once in shared memory, 16 at a time, and read by
 // every thread), then written to shared memory and factorised there (right-looking, two barriers per column);
 // the two triangular solves are done by one warp.  Rows without entries are left as the reference leaves them.
-#include "sweep.h"
-#include "device_utils.cuh"
+#include "cg_row.cuh"
 
 namespace cmfb200 {
 
@@ -23,7 +22,7 @@ constexpr int NB = 16;       // stored entries staged per round
 
 // NT threads per block, TPT register tiles per thread; MG: the kd x kd matrix does not fit in shared memory
 // and lives in a per-block slice of a global workspace instead (it stays in L2).
-template <typename T, int NT, int TPT, bool IMPLICIT, bool MG>
+template <typename T, int NT, int TPT, int MODEL, bool MG>
 __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, int kd, int kdp, int ntile_rows,
                                                         T *__restrict__ workspace)
 {
@@ -37,6 +36,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
     T *diag = colbuf + kdp;                          // [kdp]       diagonal of L
     unsigned short *tile_map = reinterpret_cast<unsigned short *>(diag + kdp);   // [ntiles][2]
 
+    constexpr bool IMPLICIT = MODEL == kModelImplicit;
     const int tid = threadIdx.x;
     const int kk = p.kk;
     const bool hb = !IMPLICIT && p.solve_bias;
@@ -61,16 +61,18 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
         const size_t beg = p.X.ptr[row];
         const int nnz = (int)(p.X.ptr[row + 1] - beg);
         T *frow = p.F + (size_t)row * (size_t)p.ldF;
-        if (nnz <= 0) {
-            if (IMPLICIT) {
-                for (int c = tid; c < kk; c += NT) frow[c] = T(0);       // A := 0 up front (src/common.c:3334)
+        if (nnz <= 0 && !(MODEL == kModelCollective && p.solve_all_rows)) {
+            if (IMPLICIT || MODEL == kModelCollective) {
+                // implicit: A := 0 up front (src/common.c:3334); collective without any information: zeroed too
+                for (int c = tid; c < kk; c += NT) frow[c] = T(0);
+                if (MODEL == kModelCollective && hb && tid == 0) frow[kk] = T(0);
             } else if (hb && p.bias_start_one && tid == 0) {
                 frow[kk] = T(1);                                         // see sweep_cg.cu
             }
             continue;
         }
         T lam = p.lam, lam_last = p.lam_last;
-        if (!IMPLICIT && p.scale_lam) {
+        if (!IMPLICIT && p.scale_lam && nnz > 0) {
             lam *= (T)nnz;
             if (!p.scale_bias_const) lam_last *= (T)nnz;
         }
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
                         const int a = 4 * my_ti[s] + i, b = 4 * my_tj[s] + j;
                         if (a < kd && b < kd) {
                             T v = acc[s][i][j];
-                            if (IMPLICIT) v += p.gram[(size_t)a * kk + b];
+                            if (MODEL != kModelExplicit && p.gram && a < kk && b < kk) v += p.gram[(size_t)a * kk + b];
                             if (a == b) v += (hb && a == kd - 1) ? lam_last : lam;
                             if (a <= b) {
                                 M[b * kdp + a] = v;   // lower triangle is what the factorisation uses
@@ -156,7 +158,10 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
                     }
             }
         }
-        if (tid < kd) rhs[tid] = rhs_acc;
+        if (tid < kd) {
+            if (MODEL == kModelCollective && p.qvec && tid < kk) rhs_acc += p.qvec[(size_t)row * (size_t)p.ldq + tid];
+            rhs[tid] = rhs_acc;
+        }
         __syncthreads();
 
         // ---- Cholesky, lower, right-looking
@@ -225,11 +230,11 @@ template <typename T> T *chol_workspace(size_t elems)
     return buf[dev];
 }
 
-template <typename T, int NT, int TPT, bool IMPLICIT, bool MG>
+template <typename T, int NT, int TPT, int MODEL, bool MG>
 int launch_tpt(const CgSweepParams &p, int kd, int kdp, int ntile_rows, cudaStream_t stream)
 {
     const size_t smem = chol_smem_bytes<T>(kd, kdp, ntile_rows, !MG);
-    auto kern = chol_sweep_kernel<T, NT, TPT, IMPLICIT, MG>;
+    auto kern = chol_sweep_kernel<T, NT, TPT, MODEL, MG>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 2;
@@ -251,10 +256,10 @@ int launch_tpt(const CgSweepParams &p, int kd, int kdp, int ntile_rows, cudaStre
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-template <bool IMPLICIT> int dispatch_chol(const CgSweepParams &p, cudaStream_t stream)
+template <int MODEL> int dispatch_chol(const CgSweepParams &p, cudaStream_t stream)
 {
     typedef real_t T;
-    const int kd = p.kk + ((!IMPLICIT && p.solve_bias) ? 1 : 0);
+    const int kd = p.kk + ((MODEL != kModelImplicit && p.solve_bias) ? 1 : 0);
     const int ntile_rows = (kd + 3) / 4;
     int kdp = ntile_rows * 4;
     if ((kdp & 31) == 0) kdp += 4;   // keep consecutive rows of M off the same banks
@@ -263,27 +268,31 @@ template <bool IMPLICIT> int dispatch_chol(const CgSweepParams &p, cudaStream_t 
     const int tpt256 = (ntiles + 255) / 256;
     const int tpt512 = (ntiles + 511) / 512;
     if (in_smem) {
-        if (tpt256 <= 1) return launch_tpt<T, 256, 1, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
-        if (tpt256 <= 2) return launch_tpt<T, 256, 2, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
-        if (tpt256 <= 3) return launch_tpt<T, 256, 3, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
-        if (tpt512 <= 2) return launch_tpt<T, 512, 2, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
-        if (tpt512 <= 3) return launch_tpt<T, 512, 3, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt256 <= 1) return launch_tpt<T, 256, 1, MODEL, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt256 <= 2) return launch_tpt<T, 256, 2, MODEL, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt256 <= 3) return launch_tpt<T, 256, 3, MODEL, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt512 <= 2) return launch_tpt<T, 512, 2, MODEL, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt512 <= 3) return launch_tpt<T, 512, 3, MODEL, false>(p, kd, kdp, ntile_rows, stream);
 #ifdef USE_FLOAT
-        if (tpt512 <= 5) return launch_tpt<T, 512, 5, IMPLICIT, false>(p, kd, kdp, ntile_rows, stream);
+        if (tpt512 <= 5) return launch_tpt<T, 512, 5, MODEL, false>(p, kd, kdp, ntile_rows, stream);
 #endif
         return 2;
     }
-    if (tpt512 <= 2) return launch_tpt<T, 512, 2, IMPLICIT, true>(p, kd, kdp, ntile_rows, stream);
-    if (tpt512 <= 3) return launch_tpt<T, 512, 3, IMPLICIT, true>(p, kd, kdp, ntile_rows, stream);
+    if (tpt512 <= 2) return launch_tpt<T, 512, 2, MODEL, true>(p, kd, kdp, ntile_rows, stream);
+    if (tpt512 <= 3) return launch_tpt<T, 512, 3, MODEL, true>(p, kd, kdp, ntile_rows, stream);
 #ifdef USE_FLOAT
-    if (tpt512 <= 5) return launch_tpt<T, 512, 5, IMPLICIT, true>(p, kd, kdp, ntile_rows, stream);
+    if (tpt512 <= 5) return launch_tpt<T, 512, 5, MODEL, true>(p, kd, kdp, ntile_rows, stream);
 #endif
     return 2;   // fp32: k up to ~280, fp64: k up to ~215
 }
 
 }  // namespace
 
-int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch_chol<false>(p, stream); }
-int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch_chol<true>(p, stream); }
+int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream)
+{
+    return (p.gram || p.qvec || p.solve_all_rows) ? dispatch_chol<kModelCollective>(p, stream)
+                                                  : dispatch_chol<kModelExplicit>(p, stream);
+}
+int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch_chol<kModelImplicit>(p, stream); }
 
 }  // namespace cmfb200

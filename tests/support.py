@@ -38,7 +38,8 @@ def synth_coo(m, n, nnz, dtype, seed=0, kind="ratings", dedup=True, zipf=True):
 
 def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, item_bias=True, center=True,
                  scale_lam=False, niter=3, use_cg=True, max_cg_steps=3, finalize_chol=False, seed=1, nthreads=4,
-                 w_main=1.0, lam_unique=None, precompute=False, k_main=0):
+                 w_main=1.0, lam_unique=None, precompute=False, k_main=0, U=None, I=None, add_implicit_features=False,
+                 w_user=1.0, w_item=1.0, w_implicit=1.0, center_side=True):
     """Call fit_collective_explicit_als (reference src/cmfrec.h:1851) on `lib`; returns dict of outputs."""
     dt = np.dtype(dtype)
     kk = k + k_main
@@ -58,15 +59,26 @@ def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, 
     ixA = np.ascontiguousarray(ixA, np.int32).copy()
     ixB = np.ascontiguousarray(ixB, np.int32).copy()
     X = np.ascontiguousarray(X, dt).copy()
+    p = 0 if U is None else U.shape[1]
+    q = 0 if I is None else I.shape[1]
+    Uc = None if U is None else np.ascontiguousarray(U, dt).copy()
+    Ic = None if I is None else np.ascontiguousarray(I, dt).copy()
+    C = np.zeros((p, k), dt) if p else None
+    D = np.zeros((q, k), dt) if q else None
+    Ai = np.zeros((m, k), dt) if add_implicit_features else None
+    Bi = np.zeros((n, k), dt) if add_implicit_features else None
+    Ucm = np.zeros(p, dt) if (p and center_side) else None
+    Icm = np.zeros(q, dt) if (q and center_side) else None
     rc = lib.fit_collective_explicit_als(
-        ptr(biasA) if user_bias else None, ptr(biasB) if item_bias else None, ptr(A), ptr(B), None, None, None, None,
-        False, True, seed, ptr(glob_mean), None, None, m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size, None, None,
-        user_bias, item_bias, center, lam, ptr(lu), 0.0, None, scale_lam, False, False, ptr(sA), ptr(sB),
-        None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False, False,
-        k_main, 0, 0, w_main, 1.0, 1.0, 1.0, niter, nthreads, False, False, use_cg, max_cg_steps, False, finalize_chol,
-        False, 100, False, False, precompute, True, ptr(Bpb), ptr(BtB), ptr(TBt), None, None, None, None, None, None)
+        ptr(biasA) if user_bias else None, ptr(biasB) if item_bias else None, ptr(A), ptr(B), ptr(C), ptr(D), ptr(Ai), ptr(Bi),
+        add_implicit_features, True, seed, ptr(glob_mean), ptr(Ucm), ptr(Icm), m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size,
+        None, None, user_bias, item_bias, center, lam, ptr(lu), 0.0, None, scale_lam, False, False, ptr(sA), ptr(sB),
+        ptr(Uc), m if p else 0, p, ptr(Ic), n if q else 0, q, None, None, None, 0, None, None, None, 0, False, False, False,
+        k_main, 0, 0, w_main, w_user, w_item, w_implicit, niter, nthreads, False, False, use_cg, max_cg_steps, False,
+        finalize_chol, False, 100, False, False, precompute, True, ptr(Bpb), ptr(BtB), ptr(TBt), None, None, None, None, None,
+        None)
     return dict(rc=rc, A=A, B=B, biasA=biasA, biasB=biasB, glob_mean=glob_mean[0], B_plus_bias=Bpb, BtB=BtB,
-                TransBtBinvBt=TBt)
+                TransBtBinvBt=TBt, C=C, D=D, Ai=Ai, Bi=Bi, U_colmeans=Ucm, I_colmeans=Icm)
 
 
 def fit_implicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=5.0, alpha=1.0, niter=3, use_cg=True, max_cg_steps=3,

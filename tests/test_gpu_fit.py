@@ -75,6 +75,48 @@ def test_explicit_fit_matches_reference(gpu_libs, dtype, case):
         assert rows_match(a["biasB"][:, None], b["biasB"][:, None], tol * max(1.0, s / np.abs(b["biasB"]).max()))
 
 
+CASES_COLLECTIVE = [
+    dict(side="UI", use_cg=False),                                 # config-3 style: Cholesky + dense U and I
+    dict(side="UI", use_cg=False, w_user=1.7, w_item=0.6, scale_lam=True, lam=0.05),
+    dict(side="UI"),                                               # CG with side information
+    dict(side="U", finalize_chol=True),
+    dict(side="I", user_bias=False, item_bias=False, center=False),
+    dict(side="", add_implicit_features=True),                     # config-4 style: CG + implicit features
+    dict(side="", add_implicit_features=True, use_cg=False, w_implicit=0.5),
+    dict(side="", add_implicit_features=True, scale_lam=True, lam=0.05, w_implicit=0.5),
+    dict(side="UI", add_implicit_features=True, w_main=2.0, finalize_chol=True),
+    dict(side="U", center_side=False, lam_unique=[0.3, 0.2, 0.07, 0.09, 0.5, 0.6]),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", range(len(CASES_COLLECTIVE)))
+def test_collective_fit_matches_reference(gpu_libs, dtype, case):
+    """side information (dense U / I) and implicit features: C, D, Ai, Bi, A, B against the reference"""
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    kw = dict(lam=1.0, niter=3, nthreads=4)
+    kw.update(CASES_COLLECTIVE[case])
+    side = kw.pop("side")
+    m, n, k = 900, 500, 12
+    ixA, ixB, X = synth_coo(m, n, 25000, dt, seed=50 + case)
+    rng = np.random.default_rng(case)
+    if "U" in side:
+        kw["U"] = rng.normal(size=(m, 7)).astype(dt) + 0.3
+    if "I" in side:
+        kw["I"] = rng.normal(size=(n, 5)).astype(dt) - 0.2
+    a = fit_explicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+    b = fit_explicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+    assert a["rc"] == 0 and b["rc"] == 0
+    tol = TOL[dt] * (1 if dt == np.float32 else 10)
+    for key in ("U_colmeans", "I_colmeans"):
+        if b[key] is not None:
+            assert np.array_equal(a[key], b[key]), key
+    for key in ("A", "B", "C", "D", "Ai", "Bi"):
+        if b[key] is not None:
+            assert rows_match(a[key], b[key], tol, 0.01), (key, rel_err(a[key], b[key]))
+
+
 CASES_IMPLICIT = [
     dict(),
     dict(alpha=40.0, lam=1.0),
@@ -149,6 +191,8 @@ def test_unsupported_arguments_are_refused(gpu_libs):
     from support import ptr
     A = np.zeros((m, k)); B = np.zeros((n, k)); g = np.zeros(1)
     w = np.ones(X.size)
+    U = np.zeros((m + 3, 2))
+    assert fit_explicit(L, dt, ixA, ixB, X, m, n, k, U=np.full((m, 2), np.nan))["rc"] == 2     # missing values in U
     rc = L.fit_collective_explicit_als(
         None, None, ptr(A), ptr(B), None, None, None, None, False, True, 1, ptr(g), None, None, m, n, k,
         ptr(ixA), ptr(ixB), ptr(X), X.size, None, ptr(w), False, False, True, 1.0, None, 0.0, None, False, False, False,
