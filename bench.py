@@ -39,6 +39,11 @@ WORKLOADS = {
     "lastfm_implicit_cg_k128_f32": dict(shape="lastfm", implicit=True, k=128, dtype="f32", use_cg=True),
     "lastfm_implicit_cg_k256_f32": dict(shape="lastfm", implicit=True, k=256, dtype="f32", use_cg=True),
     "cfg1_explicit_cg_k16_f64": dict(shape="cfg1", implicit=False, k=16, dtype="f64", use_cg=True),
+    # BASELINE.json config 3: Cholesky, fp64, k=128, dense user and item side information (p = q = 32, N(0,1), seed 3)
+    "ml10m_explicit_chol_k128_f64_sideinfo": dict(shape="ml10m", implicit=False, k=128, dtype="f64", use_cg=False, side=32),
+    # BASELINE.json config 4: CG, fp32, k=64, add_implicit_features (w_implicit = 0.5)
+    "ml10m_explicit_cg_k64_f32_implicit_features": dict(shape="ml10m", implicit=False, k=64, dtype="f32", use_cg=True,
+                                                        implicit_features=True, w_implicit=0.5),
 }
 HYPER = dict(explicit=dict(lam=0.05, scale_lam=True, user_bias=True, item_bias=True, center=True, max_cg_steps=3),
              implicit=dict(lam=5.0, alpha=1.0, max_cg_steps=3))
@@ -60,12 +65,21 @@ def load_data(w):
     return a, b, x, m, n, dt
 
 
+def side_info(w, m, n, dt):
+    if not w.get("side"):
+        return None, None
+    rng = np.random.default_rng(3)
+    return rng.normal(size=(m, w["side"])).astype(dt), rng.normal(size=(n, w["side"])).astype(dt)
+
+
 def algorithmic_bytes(w, m, n, nnz, dt):
     """every stored entry gathers its opposing row once per half-sweep, plus CSR index+value,
     plus indptr and read+write of the solved row; implicit adds one pass over the opposing factor for the Gram."""
     wd = dt.itemsize
     k1 = w["k"] + (0 if w["implicit"] else 1)
-    half = lambda rows, opp: nnz * (k1 * wd + 4 + wd) + rows * (8 + 2 * k1 * wd) + (opp * w["k"] * wd if w["implicit"] else 0)
+    extra_gather = w["k"] * wd if w.get("implicit_features") else 0      # the q-vector gathers one Bi row per entry
+    half = lambda rows, opp: (nnz * (k1 * wd + 4 + wd + extra_gather) + rows * (8 + 2 * k1 * wd)
+                              + (opp * w["k"] * wd if w["implicit"] else 0) + rows * w.get("side", 0) * wd)
     return half(n, m), half(m, n)       # (B sweep, A sweep)
 
 
@@ -135,13 +149,20 @@ def time_reference(w, data, steps, warmup, nthreads):
                                       use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthreads)
     else:
         h = HYPER["explicit"]
+        U, I = side_info(w, m, n, dt)
+        extra = dict(U=U, I=I, add_implicit_features=bool(w.get("implicit_features")), w_implicit=w.get("w_implicit", 1.0))
         run = lambda it: fit_explicit(R, dt, a, b, x, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"], niter=it,
-                                      use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthreads)
+                                      use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthreads, **extra)
     run(max(1, min(warmup, 1)))
     t0 = time.perf_counter(); run(0); t_prep = time.perf_counter() - t0
     t0 = time.perf_counter(); out = run(steps); t_full = time.perf_counter() - t0
     assert out["rc"] == 0
-    sec_iter = max(t_full - t_prep, 1e-9) / steps
+    if t_full - t_prep < 0.2 * t_full:      # too short to time by difference: repeat with many more iterations
+        big = steps * 200
+        t0 = time.perf_counter(); run(big); t_big = time.perf_counter() - t0
+        sec_iter = max(t_big - t_prep, 1e-9) / big
+    else:
+        sec_iter = max(t_full - t_prep, 1e-9) / steps
     return dict(sec_iter=sec_iter, rows_per_s=(m + n) / sec_iter, kind=kind, prep_s=t_prep, call_s=t_full,
                 call_rows_per_s=(m + n) * steps / t_full,
                 sample="full workload, one fit call of %d ALS iterations, nthreads=%d" % (steps, nthreads))
@@ -223,7 +244,8 @@ def main():
         bA = np.zeros(m, dt); bB = np.zeros(n, dt)
         L.cmfb200_init_biases_twosided(m, n, *[ptr(t) for t in csr], h["lam"], h["lam"], h["scale_lam"], False, ptr(bA), ptr(bB), ncpu)
         A0 = np.zeros((m, w["k"]), dt); B0 = np.zeros((n, w["k"]), dt)
-        L.cmfb200_random_init(ptr(A0), A0.size, None, 0, 1, True)
+        fill_B = bool(w.get("side") or w.get("implicit_features"))
+        L.cmfb200_random_init(ptr(A0), A0.size, ptr(B0) if fill_B else None, B0.size if fill_B else 0, 1, True)
         lamA = lamB = lbA = lbB = h["lam"]
 
     stream = torch.cuda.current_stream().cuda_stream
@@ -251,6 +273,17 @@ def main():
     rc = L.cmfb200_als_create(C.byref(hnd), C.byref(opt), *[ptr(t) for t in csr])
     assert rc == 0, "cmfb200_als_create -> %d" % rc
     assert L.cmfb200_als_set_factors(hnd, ptr(A0), ptr(bA), ptr(B0), ptr(bB)) == 0
+    if w.get("side") or w.get("implicit_features"):
+        assert world == 1, "side information / implicit features are single-GPU in this round"
+        U, I = side_info(w, m, n, dt)
+        if U is not None:
+            U = (U - U.mean(axis=0, dtype=dt)).astype(dt); I = (I - I.mean(axis=0, dtype=dt)).astype(dt)
+        wi = w.get("w_implicit", 1.0)
+        sm, sn = (float(m), float(n)) if h["scale_lam"] else (1.0, 1.0)
+        rc = L.cmfb200_als_attach_collective(hnd, ptr(U), w.get("side", 0), ptr(I), w.get("side", 0),
+                                             int(bool(w.get("implicit_features"))), 1.0, 1.0, wi, h["lam"] * sm, h["lam"] * sn,
+                                             h["lam"] / wi * sm, h["lam"] / wi * sn)
+        assert rc == 0, "attach_collective -> %d" % rc
     use_cg = int(w["use_cg"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -320,8 +353,11 @@ def main():
                 run = lambda nit: fit_implicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=nit,
                                                use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu)
             else:
+                U, I = side_info(w, m, n, dt)
+                extra = dict(U=U, I=I, add_implicit_features=bool(w.get("implicit_features")), w_implicit=w.get("w_implicit", 1.0))
                 run = lambda nit: fit_explicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
-                                               niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu)
+                                               niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
+                                               **extra)
             run(1)
             run(2)
             torch.cuda.synchronize()

@@ -115,7 +115,7 @@ PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
     "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_partition_rows", "cmfb200_nccl_unique_id", "cmfb200_als_create",
     "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
     "cmfb200_als_iterate", "cmfb200_als_timed_iterate", "cmfb200_als_set_profile",
-    "cmfb200_als_read_profile", "cmfb200_als_sync", "cmfb200_als_launch_count", "cmfb200_als_local_counts",
+    "cmfb200_als_read_profile", "cmfb200_als_attach_collective", "cmfb200_als_get_collective", "cmfb200_als_sync", "cmfb200_als_launch_count", "cmfb200_als_local_counts",
 )
 
 
@@ -174,6 +174,10 @@ def bind_product(lib, dtype):
     lib.cmfb200_als_set_profile.argtypes = [P, c_int]
     lib.cmfb200_als_read_profile.restype = c_int
     lib.cmfb200_als_read_profile.argtypes = [P, c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.cmfb200_als_attach_collective.restype = c_int
+    lib.cmfb200_als_attach_collective.argtypes = [P, P, c_int, P, c_int, c_int, real, real, real, real, real, real, real]
+    lib.cmfb200_als_get_collective.restype = c_int
+    lib.cmfb200_als_get_collective.argtypes = [P, P, P, P, P]
     lib.cmfb200_als_sync.restype = c_int
     lib.cmfb200_als_sync.argtypes = [P]
     lib.cmfb200_als_launch_count.restype = C.c_longlong

@@ -2,6 +2,7 @@
 #include "als.h"
 #include "nccl_link.h"
 #include "device_prep.h"
+#include "collective.h"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -128,6 +129,7 @@ AlsState::~AlsState()
 {
     for (auto &v : sweep_events)
         for (auto &pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    delete coll;
     delete link;
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -460,6 +462,10 @@ int AlsState::iterate(int first_iter, int n_iters, int niter_total, bool use_cg,
         // the reference switches the last iteration to the exact solver (src/collective.c:8336-8340)
         const bool cg_now = use_cg && !(finalize_chol && it == niter_total - 1);
         const int solver = cg_now ? 0 : 1;
+        if (coll) {
+            if (int rcc = coll->iteration(it, solver)) return rcc;
+            continue;
+        }
         int rc = half_sweep(0, it, solver);
         if (rc) return rc;
         if ((rc = exchange(0))) return rc;

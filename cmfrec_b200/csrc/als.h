@@ -66,6 +66,7 @@ struct AlsConfig {
 void build_renumbering(const size_t *ptr, int_t rows, int world, Renumbering &ren);
 
 class NcclLink;
+class CollectiveState;
 
 class AlsState {
 public:
@@ -79,6 +80,7 @@ public:
     DevBuf<real_t> A, B;          // [rows_padded x ld], device numbering
     DevBuf<real_t> gram, gram_ws;
     NcclLink *link = nullptr;
+    CollectiveState *coll = nullptr;   // attached side information / implicit features (collective.cu); owned
     // explicit model with side information / implicit features (collective.cu): constant matrix and per-row vector
     // added to the systems of the rows of B ([0]) / of A ([1]); rows without entries are solved too when set
     const real_t *extraQ[2] = {nullptr, nullptr};

@@ -4,6 +4,7 @@
 #include "../../include/cmfrec_b200.h"
 #include <cstdio>
 #include "als.h"
+#include "collective.h"
 #include "fit.h"
 #include "host_prep.h"
 #include "nccl_link.h"
@@ -206,6 +207,30 @@ void cmfb200_als_set_profile(cmfb200_als *s, int on) { s->st.profile = on != 0; 
 int cmfb200_als_read_profile(cmfb200_als *s, int which, double *total_ms, long long *count)
 {
     return s->st.read_profile(which, total_ms, count);
+}
+
+int cmfb200_als_attach_collective(cmfb200_als *s, const real_t *U_centred, int p, const real_t *I_centred, int q,
+                                  int add_implicit_features, real_t w_user, real_t w_item, real_t w_implicit, real_t lam_C,
+                                  real_t lam_D, real_t lam_Bi, real_t lam_Ai)
+{
+    if (!s || s->st.cfg.implicit || s->st.cfg.world != 1 || s->st.coll) return 2;
+    CollectiveConfig cc;
+    cc.p = U_centred ? p : 0;
+    cc.q = I_centred ? q : 0;
+    cc.implicit_features = add_implicit_features != 0;
+    cc.w_user = w_user; cc.w_item = w_item; cc.w_implicit = w_implicit;
+    cc.lam_C = lam_C; cc.lam_D = lam_D; cc.lam_Bi = lam_Bi; cc.lam_Ai = lam_Ai;
+    CollectiveState *cs = new CollectiveState();
+    int rc = cs->setup(&s->st, cc, U_centred, I_centred);
+    if (rc) { delete cs; return rc; }
+    s->st.coll = cs;
+    return 0;
+}
+
+int cmfb200_als_get_collective(cmfb200_als *s, real_t *C, real_t *D, real_t *Ai, real_t *Bi)
+{
+    if (!s || !s->st.coll) return 2;
+    return s->st.coll->download(C, D, Ai, Bi);
 }
 
 int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }

@@ -210,6 +210,15 @@ int cmfb200_als_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_t
 /* same, bracketed by CUDA events recorded on the state's stream; *elapsed_ms = device time of the n_iters */
 int cmfb200_als_timed_iterate(cmfb200_als *s, int first_iter, int n_iters, int niter_total, int use_cg,
                               int finalize_chol, float *elapsed_ms);
+/* Turn an explicit-feedback state (single GPU) into the model with dense side information and/or implicit features:
+ * U_centred [m x p], I_centred [n x q] host matrices without missing values (NULL = absent), weights and regularisers
+ * as the reference uses them after dividing by w_main (lam_C = lam/w_user * (scale_lam ? m : 1), ...; reference
+ * src/collective.c:8358-8530).  cmfb200_als_iterate then runs the C, D, Bi, Ai, B, A order of src/collective.c:8342-8876. */
+int cmfb200_als_attach_collective(cmfb200_als *s, const real_t *U_centred, int p, const real_t *I_centred, int q,
+                                  int add_implicit_features, real_t w_user, real_t w_item, real_t w_implicit, real_t lam_C,
+                                  real_t lam_D, real_t lam_Bi, real_t lam_Ai);
+/* C [p x k], D [q x k], Ai [m x k], Bi [n x k] (NULL to skip) */
+int cmfb200_als_get_collective(cmfb200_als *s, real_t *C, real_t *D, real_t *Ai, real_t *Bi);
 /* per-launch timing of the row-solve kernel: when on, every half-sweep brackets its solve kernel with CUDA events
  * on the state's stream; read_profile synchronises, returns the summed kernel time and launch count for
  * which = 0 (B sweeps) / 1 (A sweeps) since the last read, and clears the record. */
