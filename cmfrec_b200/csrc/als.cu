@@ -174,11 +174,15 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     if (rc) return rc;
     rc = build_side(csc_p, csc_i, csc_v, renB, renA, cfg.rank, stream, byB);
     if (rc) return rc;
-    ldA = cmf_ld_for(cfg.kk + 1);
-    ldB = cmf_ld_for(cfg.kk + 1);
-    if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB)) return 1;
+    ldA = cmf_ld_for(cfg.kk);
+    ldB = cmf_ld_for(cfg.kk);
+    if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB) ||
+        !biasA.alloc(renA.rows_padded) || !biasB.alloc(renB.rows_padded))
+        return 1;
     cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream);
     cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream);
+    cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream);
+    cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream);
     if (cfg.implicit) {
         if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
     }
@@ -223,12 +227,6 @@ template <typename T> __global__ void scale_kernel(T *x, size_t n, T s)
     if (i < n) x[i] = x[i] * s;
 }
 
-template <typename T> __global__ void write_bias_slot_kernel(T *F, int ld, int kk, const T *bias, int_t rows)
-{
-    const int_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < rows) F[(size_t)r * ld + kk] = bias[r];
-}
-
 int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
                              real_t scale, cudaStream_t s)
 {
@@ -262,11 +260,15 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
     launches += 12;
     if ((rc = plan_side_from_device(byA, cfg.m, stream))) return rc;
     if ((rc = plan_side_from_device(byB, cfg.n, stream))) return rc;
-    ldA = cmf_ld_for(cfg.kk + 1);
-    ldB = cmf_ld_for(cfg.kk + 1);
-    if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB)) return 1;
+    ldA = cmf_ld_for(cfg.kk);
+    ldB = cmf_ld_for(cfg.kk);
+    if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB) ||
+        !biasA.alloc(renA.rows_padded) || !biasB.alloc(renB.rows_padded))
+        return 1;
     cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream);
     cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream);
+    cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream);
+    cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream);
     if (cfg.implicit) {
         if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
     }
@@ -275,63 +277,58 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
 
 int AlsState::init_biases_on_device(int which, real_t lam_user, real_t lam_item, bool scale_lam)
 {
-    DevBuf<real_t> bA, bB;
-    if (!bA.alloc(std::max<int_t>(cfg.m, 1)) || !bB.alloc(std::max<int_t>(cfg.n, 1))) return 1;
     int rc = 0;
-    const int threads = 256;
     if (which == 3) {
         rc = device_init_biases_twosided(cfg.m, cfg.n, byA.ptr.p, byA.idx.p, byA.val.p, byB.ptr.p, byB.idx.p, byB.val.p, lam_user,
-                                         lam_item, scale_lam, bA.p, bB.p, stream);
+                                         lam_item, scale_lam, biasA.p, biasB.p, stream);
         launches += 10;
     } else if (which == 1) {
-        rc = device_init_biases_onesided(cfg.m, byA.ptr.p, byA.val.p, lam_user, scale_lam, bA.p, stream);
+        rc = device_init_biases_onesided(cfg.m, byA.ptr.p, byA.val.p, lam_user, scale_lam, biasA.p, stream);
         launches += 1;
     } else if (which == 2) {
-        rc = device_init_biases_onesided(cfg.n, byB.ptr.p, byB.val.p, lam_item, scale_lam, bB.p, stream);
+        rc = device_init_biases_onesided(cfg.n, byB.ptr.p, byB.val.p, lam_item, scale_lam, biasB.p, stream);
         launches += 1;
     }
     if (rc) return rc;
-    if (which & 1) write_bias_slot_kernel<real_t><<<(cfg.m + threads - 1) / threads, threads, 0, stream>>>(A.p, ldA, cfg.kk, bA.p, cfg.m);
-    if (which & 2) write_bias_slot_kernel<real_t><<<(cfg.n + threads - 1) / threads, threads, 0, stream>>>(B.p, ldB, cfg.kk, bB.p, cfg.n);
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
 static void pack_factor(const real_t *h, int ldh, const real_t *hbias, int_t rows, int kk, const Renumbering &ren, int ld,
-                        std::vector<real_t> &out)
+                        std::vector<real_t> &out, std::vector<real_t> &bias_out)
 {
     out.assign((size_t)ren.rows_padded * ld, real_t(0));
+    bias_out.assign((size_t)ren.rows_padded, real_t(0));
 #pragma omp parallel for schedule(static)
     for (long long r = 0; r < (long long)rows; r++) {
         real_t *dst = out.data() + (size_t)ren.to_dev[r] * ld;
         std::memcpy(dst, h + (size_t)r * ldh, (size_t)kk * sizeof(real_t));
-        dst[kk] = hbias ? hbias[r] : real_t(0);
+        if (hbias) bias_out[ren.to_dev[r]] = hbias[r];
     }
 }
 
 int AlsState::upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb,
                              const real_t *hbiasB)
 {
-    std::vector<real_t> tmp;
-    pack_factor(hA, lda, hbiasA, cfg.m, cfg.kk, renA, ldA, tmp);
+    std::vector<real_t> tmp, tb;
+    pack_factor(hA, lda, hbiasA, cfg.m, cfg.kk, renA, ldA, tmp, tb);
     if (cudaMemcpyAsync(A.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
         return 1;
+    cudaMemcpyAsync(biasA.p, tb.data(), tb.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream);
     cudaStreamSynchronize(stream);
-    pack_factor(hB, ldb, hbiasB, cfg.n, cfg.kk, renB, ldB, tmp);
+    pack_factor(hB, ldb, hbiasB, cfg.n, cfg.kk, renB, ldB, tmp, tb);
     if (cudaMemcpyAsync(B.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
         return 1;
+    cudaMemcpyAsync(biasB.p, tb.data(), tb.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream);
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
-// bias slots of one side from a host array (identity numbering): which = 1 users, 2 items
+// biases of one side from a host array (identity numbering): which = 1 users, 2 items
 int AlsState::upload_bias(int which, const real_t *hbias)
 {
     if (cfg.world != 1 || !hbias) return 2;
-    real_t *F = which == 1 ? A.p : B.p;
-    const int ld = which == 1 ? ldA : ldB;
+    real_t *dst = which == 1 ? biasA.p : biasB.p;
     const int_t rows = which == 1 ? cfg.m : cfg.n;
-    if (cudaMemcpy2DAsync(F + cfg.kk, (size_t)ld * sizeof(real_t), hbias, sizeof(real_t), sizeof(real_t), rows,
-                          cudaMemcpyHostToDevice, stream) != cudaSuccess)
-        return 1;
+    if (cudaMemcpyAsync(dst, hbias, (size_t)rows * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
@@ -347,27 +344,30 @@ int AlsState::upload_coordinates(const real_t *hA, const real_t *hB)
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
-static void unpack_factor(const std::vector<real_t> &in, int ld, const Renumbering &ren, int_t rows, int kk, real_t *h,
-                          int ldh, real_t *hbias)
+static void unpack_factor(const std::vector<real_t> &in, const std::vector<real_t> &bias_in, int ld, const Renumbering &ren,
+                          int_t rows, int kk, real_t *h, int ldh, real_t *hbias)
 {
 #pragma omp parallel for schedule(static)
     for (long long r = 0; r < (long long)rows; r++) {
         const real_t *src = in.data() + (size_t)ren.to_dev[r] * ld;
         if (h) std::memcpy(h + (size_t)r * ldh, src, (size_t)kk * sizeof(real_t));
-        if (hbias) hbias[r] = src[kk];
+        if (hbias) hbias[r] = bias_in[ren.to_dev[r]];
     }
 }
 
 int AlsState::download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB)
 {
-    std::vector<real_t> tmp(A.n);
+    std::vector<real_t> tmp(A.n), tb(biasA.n);
     if (cudaMemcpyAsync(tmp.data(), A.p, A.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    cudaMemcpyAsync(tb.data(), biasA.p, biasA.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream);
     if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
-    unpack_factor(tmp, ldA, renA, cfg.m, cfg.kk, hA, lda, hbiasA);
+    unpack_factor(tmp, tb, ldA, renA, cfg.m, cfg.kk, hA, lda, hbiasA);
     tmp.resize(B.n);
+    tb.resize(biasB.n);
     if (cudaMemcpyAsync(tmp.data(), B.p, B.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    cudaMemcpyAsync(tb.data(), biasB.p, biasB.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream);
     if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
-    unpack_factor(tmp, ldB, renB, cfg.n, cfg.kk, hB, ldb, hbiasB);
+    unpack_factor(tmp, tb, ldB, renB, cfg.n, cfg.kk, hB, ldb, hbiasB);
     return 0;
 }
 
@@ -379,6 +379,8 @@ int AlsState::half_sweep(int which, int iter, int solver)
     p.ldF = solveA ? ldA : ldB;
     p.G = solveA ? B.p : A.p;
     p.ldG = solveA ? ldB : ldA;
+    p.Fbias = solveA ? biasA.p : biasB.p;
+    p.Gbias = solveA ? biasB.p : biasA.p;
     p.kk = cfg.kk;
     const DeviceSide &side = solveA ? byA : byB;
     p.X = side.view();
@@ -453,7 +455,14 @@ int AlsState::exchange(int which)
     const int ld = solveA ? ldA : ldB;
     const int_t block = solveA ? renA.block : renB.block;
     launches += 1;
-    return link->all_gather_inplace(F, (size_t)block * ld * sizeof(real_t), stream);
+    int rc = link->all_gather_inplace(F, (size_t)block * ld * sizeof(real_t), stream);
+    if (rc) return rc;
+    const bool has_bias = !cfg.implicit && (solveA ? cfg.user_bias : cfg.item_bias);
+    if (has_bias) {
+        launches += 1;
+        rc = link->all_gather_inplace(solveA ? biasA.p : biasB.p, (size_t)block * sizeof(real_t), stream);
+    }
+    return rc;
 }
 
 int AlsState::iterate(int first_iter, int n_iters, int niter_total, bool use_cg, bool finalize_chol)

@@ -78,6 +78,7 @@ public:
     DeviceSide byA, byB;          // byA: rows = users (CSR); byB: rows = items (CSC)
     int ldA = 0, ldB = 0;
     DevBuf<real_t> A, B;          // [rows_padded x ld], device numbering
+    DevBuf<real_t> biasA, biasB;  // [rows_padded], device numbering (zero when the side has no bias)
     DevBuf<real_t> gram, gram_ws;
     NcclLink *link = nullptr;
     CollectiveState *coll = nullptr;   // attached side information / implicit features (collective.cu); owned

@@ -191,7 +191,7 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
             a[j] = (c < kk) ? frow[c] : T(0);
         }
         const bool hb = !IMPLICIT && p.solve_bias;
-        if (hb) ab = p.bias_start_one ? T(1) : frow[kk];
+        if (hb) ab = p.bias_start_one ? T(1) : p.Fbias[row];
 
         T lam = p.lam, lam_last = p.lam_last;
         if (!IMPLICIT && p.scale_lam && nnz > 0) {   // rows without entries (collective model only) keep lam as is
@@ -270,7 +270,7 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
                     if (c < kk) frow[c] = a[j];
                 }
             }
-            if (hb && l == 0 && (changed || p.bias_start_one)) frow[kk] = ab;
+            if (hb && l == 0 && (changed || p.bias_start_one)) p.Fbias[row] = ab;
         }
     }
 
@@ -288,11 +288,11 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
                     const int c = Lay::col(l, j);
                     if (c < p.kk) frow[c] = T(0);
                 }
-                if (l == 0 && p.solve_bias) frow[p.kk] = T(0);
+                if (l == 0 && p.solve_bias) p.Fbias[row] = T(0);
             }
         } else {
             if (!IMPLICIT && p.solve_bias && p.bias_start_one && lane == 0 && wt == 0)
-                p.F[(size_t)row * (size_t)p.ldF + p.kk] = T(1);
+                p.Fbias[row] = T(1);
         }
     }
 };

@@ -17,10 +17,11 @@ typedef double real_t;
 #endif
 typedef int int_t;
 
-// Device row stride of a factor matrix holding `kk` solved coordinates plus one bias slot:
-// rows start 16-byte aligned so that a whole row is one vector/bulk copy.
-static inline int cmf_ld_for(int kk_plus_slot)
+// Device row stride of a factor matrix with `kk` coordinates per row: rows are padded to a whole number of
+// 128-byte cache lines and start line-aligned, so that a gathered row is a run of FULL lines (the gathers are
+// bound by the L1/TEX tag rate: a row that straddles lines costs extra tag look-ups on every pass).
+static inline int cmf_ld_for(int kk)
 {
-    const int q = (int)(16 / sizeof(real_t));
-    return ((kk_plus_slot + q - 1) / q) * q;
+    const int q = (int)(128 / sizeof(real_t));
+    return ((kk + q - 1) / q) * q;
 }

@@ -58,16 +58,11 @@ int CollectiveState::update_side_factor(const real_t *F, int ldF, int_t rows, co
     int rc = launch_xty(F, ldF, k, F, ldF, k, rows, G1.p, ws.p, s);
     if (rc) return rc;
     if ((rc = launch_xty(S, p, p, F, ldF, k, rows, T1.p, ws.p, s))) return rc;       // S^T F : [p x k]
-    st->launches += 4;
-    std::vector<real_t> hG((size_t)k * k), hT((size_t)p * k);
-    cudaMemcpyAsync(hG.data(), G1.p, hG.size() * sizeof(real_t), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(hT.data(), T1.p, hT.size() * sizeof(real_t), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
-    for (int i = 0; i < k; i++) hG[(size_t)i * k + i] += lam;
-    // each of the p rows of hT is a right-hand side of the k x k system (posv with p right-hand sides)
-    if (host_spd_solve_rows((size_t)k, hG.data(), hT.data(), (size_t)p)) return 1;
-    cudaMemcpyAsync(Cout, hT.data(), hT.size() * sizeof(real_t), cudaMemcpyHostToDevice, s);
-    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 1;
+    // each of the p rows of S^T F is a right-hand side of the k x k system (posv with p right-hand sides)
+    if ((rc = launch_spd_factor(G1.p, k, lam, Ldev.p, s))) return rc;
+    if ((rc = launch_tri_solve_rows(Ldev.p, k, T1.p, k, p, s))) return rc;
+    st->launches += 6;
+    return cudaMemcpyAsync(Cout, T1.p, (size_t)p * k * sizeof(real_t), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
 }
 
 // implicit-features factor: Out[r] = (F^T F + lam I)^-1 sum_{e in row r of X} F[col_e]
@@ -77,16 +72,11 @@ int CollectiveState::update_implicit_factor(const DeviceSide &side, const real_t
     cudaStream_t s = st->stream;
     int rc = launch_xty(F, ldF, k, F, ldF, k, rowsF, G1.p, ws.p, s);
     if (rc) return rc;
-    std::vector<real_t> hG((size_t)k * k), hL;
-    cudaMemcpyAsync(hG.data(), G1.p, hG.size() * sizeof(real_t), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
-    for (int i = 0; i < k; i++) hG[(size_t)i * k + i] += lam;
-    if (spd_factor_host(k, hG.data(), hL)) return 1;
-    cudaMemcpyAsync(Ldev.p, hL.data(), hL.size() * sizeof(real_t), cudaMemcpyHostToDevice, s);
+    if ((rc = launch_spd_factor(G1.p, k, lam, Ldev.p, s))) return rc;
     if ((rc = launch_spmm_ones(side.view(), side.plan(), F, ldF, k, real_t(1), false, Out, k, s))) return rc;
     if ((rc = launch_tri_solve_rows(Ldev.p, k, Out, k, side.n_order, s))) return rc;
-    st->launches += 4;
-    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 1;   // hL must outlive the copy
+    st->launches += 5;
+    return 0;
 }
 
 // Q and q for one side.  sideinfo: S [rows x p], Cfac [p x k], weight w_side; implicit: factor Fi of the opposing side

@@ -178,6 +178,37 @@ __global__ void tri_solve_rows_kernel(const T *__restrict__ Lmat, int d, T *__re
     }
 }
 
+// L := Cholesky factor (lower, row-major, zeros above the diagonal) of S + lam*I; one thread block; S full symmetric [d x d].
+// Works in place in global memory (the matrix is tiny and stays in L1/L2).
+template <typename T> __global__ void __launch_bounds__(256) spd_factor_kernel(const T *__restrict__ S, int d, T lam, T *__restrict__ Lout)
+{
+    __shared__ T dj_s;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < d * d; i += nt) {
+        const int r = i / d, c = i % d;
+        Lout[i] = (c <= r) ? S[i] + ((c == r) ? lam : T(0)) : T(0);
+    }
+    __syncthreads();
+    for (int j = 0; j < d; j++) {
+        if (tid == 0) {
+            const T v = sqrt(Lout[j * d + j]);
+            Lout[j * d + j] = v;
+            dj_s = v;
+        }
+        __syncthreads();
+        const T inv = T(1) / dj_s;
+        for (int i = j + 1 + tid; i < d; i += nt) Lout[i * d + j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: (i, c) with j < c <= i
+        const int rem = d - j - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+            if (c <= i) Lout[i * d + c] = fma(-Lout[i * d + j], Lout[c * d + j], Lout[i * d + c]);
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T> __global__ void axpby_kernel(int n, T alpha, const T *x, T beta, const T *y, T *out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,6 +290,12 @@ int spd_factor_host(int d, const real_t *S_host, std::vector<real_t> &L_host)
     L_host.resize((size_t)d * d);
     for (size_t i = 0; i < L_host.size(); i++) L_host[i] = (real_t)Lm[i];
     return 0;
+}
+
+int launch_spd_factor(const real_t *S_dev, int d, real_t lam, real_t *L_dev, cudaStream_t stream)
+{
+    spd_factor_kernel<real_t><<<1, 256, 0, stream>>>(S_dev, d, lam, L_dev);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 int launch_tri_solve_rows(const real_t *L_dev, int d, real_t *R, int ldr, int_t rows, cudaStream_t stream)

@@ -19,6 +19,8 @@ int launch_spmm_ones(const CsrView &X, const SweepPlan &plan, const real_t *F, i
                      real_t *Y, int ldy, cudaStream_t stream);
 // Cholesky factor (lower, row-major) of a small SPD matrix given on the host; computed in double
 int spd_factor_host(int d, const real_t *S_host, std::vector<real_t> &L_host);
+// L_dev := Cholesky factor (lower, row-major) of S_dev + lam*I, all on the device (single thread block)
+int launch_spd_factor(const real_t *S_dev, int d, real_t lam, real_t *L_dev, cudaStream_t stream);
 // every row of R := (L L^T)^-1 row
 int launch_tri_solve_rows(const real_t *L_dev, int d, real_t *R, int ldr, int_t rows, cudaStream_t stream);
 // out = alpha*x + beta*y (either may be null)

@@ -2,9 +2,9 @@
 // They are what the reference's optimizeA (src/common.c:2742, sparse "Case 4" :3209-3302) and
 // optimizeA_implicit (src/common.c:3305-3421) do with an OpenMP loop over rows.
 //
-// Device layout of a factor matrix F with kk latent coordinates: row-major [rows x ld], ld =
-// cmf_ld_for(kk + 1); columns 0..kk-1 hold the coordinates, column kk (the "bias slot") holds that
-// row's bias (0 when the side has none), remaining columns are zero padding.
+// Device layout of a factor matrix F with kk latent coordinates: row-major [rows x ld], ld = cmf_ld_for(kk)
+// (whole 128-byte lines); columns 0..kk-1 hold the coordinates, the rest is zero padding.  The biases of a side
+// live in a separate array indexed by row.
 #pragma once
 #include <cuda_runtime.h>
 #include "cmf_types.h"
@@ -28,13 +28,15 @@ struct SweepPlan {          // device pointers, built once per CSR by build_swee
 struct CgSweepParams {
     real_t *F; int ldF;           // factor being solved (in/out: CG is warm-started)
     const real_t *G; int ldG;     // opposing factor
+    real_t *Fbias;                // biases of the solved side [rows] (in/out), used when solve_bias
+    const real_t *Gbias;          // biases of the opposing side, used when center_opp
     int kk;                       // shared latent coordinates
     CsrView X;
     SweepPlan plan;
     real_t lam, lam_last;
     bool scale_lam, scale_bias_const;
-    bool solve_bias;              // the solved row has a bias coordinate (slot kk of F; opposing value is 1)
-    bool center_opp;              // subtract the opposing row's bias slot from every x before use
+    bool solve_bias;              // the solved row has a bias coordinate (Fbias; its opposing value is 1)
+    bool center_opp;              // subtract the opposing row's bias (Gbias) from every x before use
     bool bias_start_one;          // start the bias coordinate from 1.0 instead of the stored bias
     int max_cg_steps;
     const real_t *gram;           // constant [kk x kk] matrix (row-major, full symmetric) added to every row's system:

@@ -93,7 +93,7 @@ template <typename T, int C, int L, int TW> struct DirectGather {
                 const T *grow = p.G + (size_t)(valid ? col : 0) * (size_t)p.ldG;
                 T v[C];
                 gather_row<T, C, L>(grow, l, p.ldG, valid, v);
-                if (p.center_opp && valid) x -= __ldg(grow + kk);
+                if (KIND == kExplicitResidual && p.center_opp && valid) x -= __ldg(p.Gbias + col);
                 T d0 = T(0), d1 = T(0);
 #pragma unroll
                 for (int j = 0; j < C; j += 2) {
@@ -112,8 +112,8 @@ template <typename T, int C, int L, int TW> struct DirectGather {
     }
 };
 
-template <typename T, int C, int L, int MODEL, bool GRAM_SMEM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) cg_sweep_kernel(const CgSweepParams p)
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int MINB = 2>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) cg_sweep_kernel(const CgSweepParams p)
 {
     typedef Layout<T, C, L> Lay;
     constexpr int W = kWarpsPerBlock;
@@ -223,7 +223,7 @@ int launch_cluster_cfg(const CgSweepParams &p, int n_huge, cudaStream_t stream)
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-template <typename T, int C, int L, int MODEL>
+template <typename T, int C, int L, int MODEL, int MINB = 2>
 int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
 {
     // the first n_huge rows of the (degree-sorted) order go to the cluster kernel, the rest to the main kernel
@@ -248,7 +248,7 @@ int launch_cfg(const CgSweepParams &p_in, cudaStream_t stream)
     const int n_long = p.plan.n_long;
     const int n_slots = n_long + (p.plan.n_rows - n_long + W - 1) / W;
     if (n_slots <= 0) return 0;
-    auto kern = gram_in_smem ? cg_sweep_kernel<T, C, L, MODEL, true> : cg_sweep_kernel<T, C, L, MODEL, false>;
+    auto kern = gram_in_smem ? cg_sweep_kernel<T, C, L, MODEL, true, MINB> : cg_sweep_kernel<T, C, L, MODEL, false, MINB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem);
@@ -276,6 +276,10 @@ template <int MODEL> int dispatch(const CgSweepParams &p, cudaStream_t stream)
         const int v = e ? std::atoi(e) : 0;
         if (v == 1) return launch_cfg<float, 8, 8, MODEL>(p, stream);
         if (v == 2) return launch_cfg<float, 4, 16, MODEL>(p, stream);
+        if (v == 3) return launch_cfg<float, 16, 4, MODEL, 3>(p, stream);
+        if (v == 4) return launch_cfg<float, 16, 4, MODEL, 4>(p, stream);
+        if (v == 5) return launch_cfg<float, 8, 8, MODEL, 4>(p, stream);
+        if (v == 6) return launch_cfg<float, 8, 8, MODEL, 3>(p, stream);
         return launch_cfg<float, 16, 4, MODEL>(p, stream);   // measured fastest: 8 entries in flight per warp
     }
     if (kk <= 128) return launch_cfg<float, 8, 16, MODEL>(p, stream);

@@ -120,7 +120,9 @@ template <typename T, int C, int L, int TW> struct StagedGather {
             const int e = c * CH + local;
             if (e < rnnz) {
                 const int col = p.X.idx[rbeg + e];
-                xs[s * CH + local] = p.X.val[rbeg + e];
+                T xv = p.X.val[rbeg + e];
+                if (p.center_opp) xv -= __ldg(p.Gbias + col);   // the value is staged already reduced by the opposing bias
+                xs[s * CH + local] = xv;
                 const uint32_t bytes = (uint32_t)(p.ldG * sizeof(T));
                 mbar_arrive_expect_tx(&full[s], bytes);
                 bulk_copy_g2s(rows + ((size_t)s * CH + local) * RS, p.G + (size_t)col * (size_t)p.ldG, bytes, &full[s]);
@@ -253,7 +255,6 @@ template <typename T, int C, int L, int TW> struct StagedGather {
                     }
                 }
                 T x = valid ? xs[s * CH + local] : T(0);
-                if (p.center_opp && valid) x -= srow[kk];
                 T d0 = T(0), d1 = T(0);
 #pragma unroll
                 for (int j = 0; j < C; j += 2) {

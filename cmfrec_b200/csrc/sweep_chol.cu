@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
             if (IMPLICIT || MODEL == kModelCollective) {
                 // implicit: A := 0 up front (src/common.c:3334); collective without any information: zeroed too
                 for (int c = tid; c < kk; c += NT) frow[c] = T(0);
-                if (MODEL == kModelCollective && hb && tid == 0) frow[kk] = T(0);
+                if (MODEL == kModelCollective && hb && tid == 0) p.Fbias[row] = T(0);
             } else if (hb && p.bias_start_one && tid == 0) {
-                frow[kk] = T(1);                                         // see sweep_cg.cu
+                p.Fbias[row] = T(1);                                     // see sweep_cg.cu
             }
             continue;
         }
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
                     wgt[tid] = x;
                     xr[tid] = x + T(1);
                 } else {
-                    const T ob = p.center_opp ? __ldg(p.G + (size_t)col * p.ldG + kk) : T(0);
+                    const T ob = p.center_opp ? __ldg(p.Gbias + col) : T(0);
                     wgt[tid] = T(1);
                     xr[tid] = x - ob;
                 }
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
             }
             for (int c = lane; c < kd; c += 32) {
                 if (c < kk) frow[c] = rhs[c];
-                else frow[kk] = rhs[c];
+                else p.Fbias[row] = rhs[c];
             }
         }
         __syncthreads();
