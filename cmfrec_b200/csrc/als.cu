@@ -96,6 +96,8 @@ static int build_side(const size_t *ptr, const int_t *idx, const real_t *val, co
     while (n_long < (int_t)order.size() && hptr[order[n_long] + 1] - hptr[order[n_long]] >= thr) n_long++;
     side.n_order = (int_t)order.size();
     side.n_long = n_long;
+    side.deg_sorted.resize(order.size());
+    for (size_t i = 0; i < order.size(); i++) side.deg_sorted[i] = (int_t)(hptr[order[i] + 1] - hptr[order[i]]);
     {
         const size_t t_huge = (size_t)env_or("CMFB200_HUGE_ROW", 8192);
         int_t h = 0;
@@ -212,6 +214,8 @@ static int plan_side_from_device(DeviceSide &side, int_t rows, cudaStream_t stre
         return c;
     };
     side.n_order = rows;
+    side.deg_sorted.resize(rows);
+    for (int_t i = 0; i < rows; i++) side.deg_sorted[i] = (int_t)(hptr[order[i] + 1] - hptr[order[i]]);
     side.n_long = count_ge((size_t)long_row_threshold(), rows);
     side.n_huge = count_ge((size_t)env_or("CMFB200_HUGE_ROW", 8192), side.n_long);
     side.n_big = count_ge((size_t)env_or("CMFB200_T_BIG", 512), rows);
@@ -417,27 +421,35 @@ int AlsState::half_sweep(int which, int iter, int solver)
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    const bool fork = solver == 0 && side_stream && p.plan.n_huge > 0 && !env_or("CMFB200_STAGED", 0);
-    if (fork) {
-        // the side stream may start once everything queued so far on the main stream is done
-        cudaEventRecord(ev_fork, stream);
-        cudaStreamWaitEvent(side_stream, ev_fork, 0);
-        p.side_stream = side_stream;
-    }
     if (solver == 0) {
         rc = 3;
-        if (env_or("CMFB200_STAGED", 0) && (cfg.implicit || (!p.gram && !p.qvec && !p.solve_all_rows))) {
+        // default: rows resident in shared memory across the CG passes (sweep_cg_resident.cu)
+        if (env_or("CMFB200_RESIDENT", 1)) {
+            int nl = 0;
+            rc = cfg.implicit ? launch_implicit_cg_sweep_resident(p, stream, &nl) : launch_explicit_cg_sweep_resident(p, stream, &nl);
+            if (rc == 0) launches += nl - 1;
+        }
+        if (rc == 3 && env_or("CMFB200_STAGED", 0) && (cfg.implicit || (!p.gram && !p.qvec && !p.solve_all_rows))) {
             rc = cfg.implicit ? launch_implicit_cg_sweep_staged(p, stream) : launch_explicit_cg_sweep_staged(p, stream);
             if (rc == 0) launches += 2;
         }
-        if (rc == 3) rc = cfg.implicit ? launch_implicit_cg_sweep(p, stream) : launch_explicit_cg_sweep(p, stream);
+        if (rc == 3) {
+            // direct gathers from L2 on every pass (sweep_cg.cu); the longest rows go to a cluster kernel on a second stream
+            const bool fork = side_stream && p.plan.n_huge > 0;
+            if (fork) {
+                cudaEventRecord(ev_fork, stream);
+                cudaStreamWaitEvent(side_stream, ev_fork, 0);
+                p.side_stream = side_stream;
+            }
+            rc = cfg.implicit ? launch_implicit_cg_sweep(p, stream) : launch_explicit_cg_sweep(p, stream);
+            if (fork) {
+                cudaEventRecord(ev_join, side_stream);
+                cudaStreamWaitEvent(stream, ev_join, 0);
+                launches += 1;
+            }
+        }
     } else {
         rc = cfg.implicit ? launch_implicit_chol_sweep(p, stream) : launch_explicit_chol_sweep(p, stream);
-    }
-    if (fork) {
-        cudaEventRecord(ev_join, side_stream);
-        cudaStreamWaitEvent(stream, ev_join, 0);
-        launches += 1;
     }
     if (profile) {
         cudaEventRecord(e1, stream);

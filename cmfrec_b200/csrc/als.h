@@ -40,9 +40,10 @@ struct DeviceSide {
     DevBuf<int_t> idx;
     DevBuf<real_t> val;
     DevBuf<int_t> order;
+    std::vector<int_t> deg_sorted;   // host: stored entries of order[i], descending
     int_t n_order = 0, n_long = 0, n_huge = 0, n_big = 0, n_mid = 0;
     CsrView view() const { return CsrView{ptr.p, idx.p, val.p}; }
-    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long, n_huge, n_big, n_mid}; }
+    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long, n_huge, n_big, n_mid, deg_sorted.empty() ? nullptr : deg_sorted.data()}; }
 };
 
 struct Renumbering {              // old (caller) row id <-> device row id

@@ -24,6 +24,68 @@ template <typename T, int C, int L> struct Layout {
     __device__ __forceinline__ static int col(int l, int j) { return ((j / VN) * L + l) * VN + (j % VN); }
 };
 
+// fetch this lane's C coordinates of one opposing row (columns >= ld read as zero)
+template <typename T, int C, int L>
+__device__ __forceinline__ void gather_row(const T *row, int l, int ld, bool valid, T (&v)[C])
+{
+    typedef Layout<T, C, L> Lay;
+    if constexpr (Lay::VN > 1) {
+#pragma unroll
+        for (int q = 0; q < C / Lay::VN; q++) {
+            const int c = (q * L + l) * Lay::VN;
+            if (valid && c < ld) {
+                ldg_vec(row + c, &v[q * Lay::VN]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < Lay::VN; e++) v[q * Lay::VN + e] = T(0);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int c = j * L + l;
+            v[j] = (valid && c < ld) ? __ldg(row + c) : T(0);
+        }
+    }
+}
+
+// sum_j v[j] * w[j] as (even-index sum) + (odd-index sum); float uses the packed FMA of sm_100 (FFMA2: two
+// independent IEEE fmas per instruction, so the result is bit-identical to the scalar form and half the issue slots)
+template <int C> __device__ __forceinline__ float dot_pairs(const float (&v)[C], const float (&w)[C])
+{
+    static_assert(C % 2 == 0, "pairs");
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < C; j += 2) s = __ffma2_rn(make_float2(v[j], v[j + 1]), make_float2(w[j], w[j + 1]), s);
+    return s.x + s.y;
+}
+template <int C> __device__ __forceinline__ double dot_pairs(const double (&v)[C], const double (&w)[C])
+{
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; j += 2) {
+        d0 = fma(v[j], w[j], d0);
+        if (j + 1 < C) d1 = fma(v[j + 1], w[j + 1], d1);
+    }
+    return d0 + d1;
+}
+// acc += coef * v
+template <int C> __device__ __forceinline__ void axpy_pairs(float coef, const float (&v)[C], float (&acc)[C])
+{
+    const float2 cc = make_float2(coef, coef);
+#pragma unroll
+    for (int j = 0; j < C; j += 2) {
+        const float2 r = __ffma2_rn(cc, make_float2(v[j], v[j + 1]), make_float2(acc[j], acc[j + 1]));
+        acc[j] = r.x;
+        acc[j + 1] = r.y;
+    }
+}
+template <int C> __device__ __forceinline__ void axpy_pairs(double coef, const double (&v)[C], double (&acc)[C])
+{
+#pragma unroll
+    for (int j = 0; j < C; j++) acc[j] = fma(coef, v[j], acc[j]);
+}
+
 enum PassKind { kExplicitResidual = 0, kExplicitAp = 1, kImplicitResidual = 2, kImplicitAp = 3 };
 
 // x is the stored value (explicit: already reduced by the opposing bias), d the current prediction
@@ -61,6 +123,7 @@ constexpr int kModelExplicit = 0, kModelImplicit = 1, kModelCollective = 2;
 template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 1> struct CgRow {
     static constexpr bool IMPLICIT = MODEL == kModelImplicit;
     static constexpr bool HAS_Q = MODEL != kModelExplicit;
+    static_assert(CL == 1 || TW > 1, "a cluster team is made of whole thread blocks");
     typedef Layout<T, C, L> Lay;
     typedef TeamScratch<T, C, L, TW> Scr;
     static constexpr int G = 32 / L;
@@ -86,53 +149,50 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
 
     __device__ __forceinline__ void sync() const { team_barrier<TW>(bar_id); }
 
-    // partial sums held by every lane -> totals in every lane of the team
+    // partial sums held by every lane -> totals in every lane of the team.
+    // Warps first combine their groups with shuffles; the TW per-warp partials are then summed column-parallel
+    // (one thread per coordinate) through shared memory, and for a cluster the CL per-block totals likewise
+    // through distributed shared memory -- never every thread reading every partial.
     __device__ __forceinline__ void combine(T (&acc)[C], T &accb)
     {
 #pragma unroll
         for (int j = 0; j < C; j++) acc[j] = across_groups_sum<L>(acc[j]);
         accb = across_groups_sum<L>(accb);
         if constexpr (TW > 1) {
-            T *buf = red + phase * (TW * Scr::RED_STRIDE);
+            T *partial = red;                                      // [TW][RED_STRIDE]
+            T *total = red + (TW + phase) * Scr::RED_STRIDE;       // [RED_STRIDE], double-buffered: cluster peers read it
             if (g == 0) {
 #pragma unroll
-                for (int j = 0; j < C; j++) buf[wt * Scr::RED_STRIDE + Lay::col(l, j)] = acc[j];
-                if (l == 0) buf[wt * Scr::RED_STRIDE + Lay::KP] = accb;
+                for (int j = 0; j < C; j++) partial[wt * Scr::RED_STRIDE + Lay::col(l, j)] = acc[j];
+                if (l == 0) partial[wt * Scr::RED_STRIDE + Lay::KP] = accb;
             }
             sync();
-#pragma unroll
-            for (int j = 0; j < C; j++) {
+            const int tid = wt * 32 + lane;
+            for (int c = tid; c <= Lay::KP; c += TW * 32) {
                 T s = T(0);
 #pragma unroll
-                for (int ww = 0; ww < TW; ww++) s += buf[ww * Scr::RED_STRIDE + Lay::col(l, j)];
-                acc[j] = s;
+                for (int ww = 0; ww < TW; ww++) s += partial[ww * Scr::RED_STRIDE + c];
+                total[c] = s;
             }
-            T sb = T(0);
+            sync();
+            const T *src = total;
+            if constexpr (CL > 1) {
+                namespace cg = cooperative_groups;
+                cg::cluster_group cluster = cg::this_cluster();
+                cluster.sync();
+                T *ctot = cl_buf + phase * Scr::RED_STRIDE;
+                for (int c = tid; c <= Lay::KP; c += TW * 32) {
+                    T s = T(0);
+                    for (int r = 0; r < CL; r++) s += cluster.map_shared_rank(total, r)[c];
+                    ctot[c] = s;
+                }
+                sync();
+                src = ctot;
+            }
 #pragma unroll
-            for (int ww = 0; ww < TW; ww++) sb += buf[ww * Scr::RED_STRIDE + Lay::KP];
-            accb = sb;
+            for (int j = 0; j < C; j++) acc[j] = src[Lay::col(l, j)];
+            accb = src[Lay::KP];
             phase ^= 1;
-        }
-        if constexpr (CL > 1) {
-            namespace cg = cooperative_groups;
-            cg::cluster_group cluster = cg::this_cluster();
-            T *mine = cl_buf + cl_phase * Scr::RED_STRIDE;
-            if (g == 0 && wt == 0) {
-#pragma unroll
-                for (int j = 0; j < C; j++) mine[Lay::col(l, j)] = acc[j];
-                if (l == 0) mine[Lay::KP] = accb;
-            }
-            cluster.sync();
-#pragma unroll
-            for (int j = 0; j < C; j++) acc[j] = T(0);
-            accb = T(0);
-            for (int r = 0; r < CL; r++) {
-                const T *peer = cluster.map_shared_rank(mine, r);
-#pragma unroll
-                for (int j = 0; j < C; j++) acc[j] += peer[Lay::col(l, j)];
-                accb += peer[Lay::KP];
-            }
-            cl_phase ^= 1;
         }
     }
 

@@ -27,31 +27,6 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
-// fetch this lane's C coordinates of one opposing row (columns >= ld read as zero)
-template <typename T, int C, int L>
-__device__ __forceinline__ void gather_row(const T *row, int l, int ld, bool valid, T (&v)[C])
-{
-    typedef Layout<T, C, L> Lay;
-    if constexpr (Lay::VN > 1) {
-#pragma unroll
-        for (int q = 0; q < C / Lay::VN; q++) {
-            const int c = (q * L + l) * Lay::VN;
-            if (valid && c < ld) {
-                ldg_vec(row + c, &v[q * Lay::VN]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < Lay::VN; e++) v[q * Lay::VN + e] = T(0);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < C; j++) {
-            const int c = j * L + l;
-            v[j] = (valid && c < ld) ? __ldg(row + c) : T(0);
-        }
-    }
-}
-
 // Entries of the row read straight from global memory (L2 for the opposing factor): every pass re-gathers.
 // The team's warps take 32-entry chunks round-robin; inside a warp each of the 32/L groups owns one entry at a time.
 template <typename T, int C, int L, int TW> struct DirectGather {

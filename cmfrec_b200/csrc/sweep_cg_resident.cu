@@ -1,0 +1,551 @@
+// Conjugate-gradient half-sweep with the gathered opposing-factor rows RESIDENT IN SHARED MEMORY.
+//
+// The CG of one row makes 1 + max_cg_steps passes over the row's stored entries, and every pass needs the
+// opposing-factor row of every entry.  The direct kernel (sweep_cg.cu) re-gathers them from L2 on every pass
+// and is bound by the L1/LSU wavefront rate and by L2 bandwidth (profiles/).  Here every warp copies the
+// opposing rows of ITS entries into its own slice of shared memory ONCE (16-byte cp.async, SASS LDGSTS, L1
+// bypassed) and all passes read shared memory: the single-gather traffic model of SURVEY.md 8(d).
+//
+// A row is solved by a team whose size is picked from the row's number of stored entries so that the row fits
+// the team's shared memory:  1, 2, 4 or 8 warps of one thread block, or a cluster of 2, 4 or 8 thread blocks
+// (per-pass sums combined through distributed shared memory).  Entries are dealt to the warps of a team in
+// contiguous equal shares; the assignment is the same in every pass, so a warp only ever reads what it
+// staged itself and staging needs no block-level synchronisation.  Entries beyond a warp's capacity (only in
+// rows longer than the largest team holds) are streamed from L2 on every pass as in the direct kernel.
+//
+// The CG algebra is cg_row.cuh (shared with the direct kernel): reference factors_explicit_cg
+// (src/common.c:1098-1188), factors_implicit_cg (src/common.c:1914-1986), collective_block_cg
+// (src/collective.c:2134-2902).
+#include "cg_row.cuh"
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+
+namespace cmfb200 {
+
+namespace {
+
+constexpr int kW = 8;   // warps per thread block
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gather policy: this warp's entries come from its shared-memory region (first `cap` of them) or from L2
+// ---------------------------------------------------------------------------------------------------------
+// STREAM = false compiles the L2 path out (teams whose rows always fit)
+template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
+    typedef Layout<T, C, L> Lay;
+    typedef typename VecOf<T>::type Vec;
+    static constexpr int G = 32 / L;
+    static constexpr int VN = VecOf<T>::N;     // elements per 16 bytes
+    static_assert(Lay::VN == VN, "the lane layout must be made of 16-byte pieces");
+    static constexpr int KP = Lay::KP;
+    // 4-lane groups read 64 bytes each and two of them share a quarter-warp: with a row stride of 16 (mod 32)
+    // bytes and the two groups taking entries 4 apart their reads fall on disjoint banks.  Wider groups read
+    // whole 128-byte bank rows and never conflict.
+    static constexpr int PAD = (L == 4) ? VN : 0;
+    static constexpr int RS = KP + PAD;        // elements between staged rows
+    static constexpr int U = KP / VN;          // 16-byte pieces per staged row
+    static constexpr size_t kEntryBytes = (size_t)(RS + 1) * sizeof(T);   // staged row + staged value
+
+    const CgSweepParams &p;
+    T *rows;          // [cap][RS]
+    T *xs;            // [cap]   stored value, already reduced by the opposing bias (explicit model)
+    int cap;          // resident entries of this warp (multiple of 8)
+    size_t beg;       // first entry of this warp's share of the row
+    int nnz;          // entries in this warp's share
+    int gw, GW;       // index of this warp in its team / number of warps in the team (all blocks of a cluster)
+    int lane, g, l, gi;
+
+    __device__ __forceinline__ ResidentGather(const CgSweepParams &p_, T *region, int cap_, int gw_, int GW_)
+        : p(p_), rows(region), xs(region + (size_t)cap_ * RS), cap(cap_), beg(0), nnz(0), gw(gw_), GW(GW_)
+    {
+        lane = threadIdx.x & 31;
+        g = lane / L;
+        l = lane % L;
+        gi = (L == 4) ? ((g >> 1) + (G / 2) * (g & 1)) : g;
+    }
+
+    // The row's entries are dealt to the team's warps in contiguous, equal shares (a multiple of 8 entries each,
+    // so a row of at most GW * cap entries is resident in full)
+    __device__ __forceinline__ void begin(size_t row_beg, int row_nnz)
+    {
+        const int per = ((row_nnz + GW * 8 - 1) / (GW * 8)) * 8;
+        const int first = gw * per;
+        int mine = row_nnz - first;
+        if (mine > per) mine = per;
+        if (mine < 0) mine = 0;
+        beg = row_beg + (size_t)(mine > 0 ? first : 0);
+        nnz = mine;
+    }
+
+    // copy the opposing rows of this warp's first `cap` entries into its region
+    __device__ __forceinline__ void stage()
+    {
+        __syncwarp();
+        const int ldG = p.ldG;
+        for (int i = 0; i * 32 < nnz && i * 32 < cap; i++) {
+            const int e = i * 32 + lane;
+            const int slot = e;
+            int col = -1;
+            if (e < nnz && slot < cap) {
+                col = p.X.idx[beg + e];
+                T x = p.X.val[beg + e];
+                if (p.center_opp) x -= __ldg(p.Gbias + col);
+                xs[slot] = x;
+            }
+#pragma unroll 4
+            for (int j = 0; j < U; j++) {
+                const int u = j * 32 + lane;
+                const int ent = u / U, part = u % U;
+                const int c = __shfl_sync(CMF_FULL_MASK, col, ent);
+                if (c >= 0 && part * VN < ldG)
+                    cp_async_16(rows + (size_t)(i * 32 + ent) * RS + part * VN, p.G + (size_t)c * (size_t)ldG + part * VN);
+            }
+        }
+        // slots between the share's last entry and the end of its last group of G are read by the passes: zero them
+        // (everything else a pass reads was either staged above or zeroed when the kernel started)
+        {
+            const int res = nnz < cap ? nnz : cap;
+            const int tail_end = (res + G - 1) / G * G;
+            for (int u = res * RS + lane; u < tail_end * RS; u += 32) rows[u] = T(0);
+            if (res + lane < tail_end) xs[res + lane] = T(0);
+        }
+        cp_async_commit_wait_all();
+        __syncwarp();
+    }
+
+    // once per kernel: columns the staging never writes (>= ldG) must read as zero
+    __device__ __forceinline__ void clear_region()
+    {
+        for (int u = lane; u < cap * (RS + 1); u += 32) rows[u] = T(0);
+        __syncwarp();
+    }
+
+    template <int KIND>
+    __device__ __forceinline__ void pass(const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
+    {
+        const int ldG = p.ldG;
+        for (int i = 0; i * 32 < nnz; i++) {
+            const int li0 = i * 32;
+            const int left = nnz - li0;       // entries from this chunk on (may exceed 32)
+            int col_r = -1;
+            T x_r = T(0);
+            if constexpr (STREAM) {
+                if (li0 + 32 > cap) {         // warp-uniform: part of the chunk is not resident
+                    const int e = li0 + lane;
+                    if (e < nnz) {
+                        col_r = p.X.idx[beg + e];
+                        x_r = p.X.val[beg + e];
+                    }
+                }
+            }
+#pragma unroll 4
+            for (int t = 0; t < L; t++) {
+                if (t * G >= left) break;     // warp-uniform
+                const int ent = t * G + gi;
+                const bool valid = ent < left;
+                T v[C];
+                T x = T(0);
+                if (!STREAM || li0 + t * G < cap) {   // warp-uniform: these G entries are resident
+                    const int slot = li0 + ent;
+                    const T *srow = rows + (size_t)slot * RS;
+#pragma unroll
+                    for (int q = 0; q < C / VN; q++) {
+                        const Vec vv = *reinterpret_cast<const Vec *>(srow + (q * L + l) * VN);
+                        const T *pv = reinterpret_cast<const T *>(&vv);
+#pragma unroll
+                        for (int e2 = 0; e2 < VN; e2++) v[q * VN + e2] = pv[e2];
+                    }
+                    x = xs[slot];
+                } else if constexpr (STREAM) {
+                    const int col = __shfl_sync(CMF_FULL_MASK, col_r, ent);
+                    x = __shfl_sync(CMF_FULL_MASK, x_r, ent);
+                    const bool ok = col >= 0;
+                    const T *grow = p.G + (size_t)(ok ? col : 0) * (size_t)ldG;
+                    gather_row<T, C, L>(grow, l, ldG, ok, v);
+                    if (KIND == kExplicitResidual && p.center_opp && ok) x -= __ldg(p.Gbias + col);
+                }
+                T d = group_sum<L>(dot_pairs<C>(v, vec));
+                d += vecb;   // opposing value of the bias coordinate is 1 (vecb is 0 when there is none)
+                T coef = entry_coef<KIND>(d, x);
+                if (!valid) coef = T(0);
+                axpy_pairs<C>(coef, v, acc);
+                accb += coef;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+struct ResidentPlan {
+    // positions in the degree-sorted row list: [b8,b4) 8-warp teams, [b4,b2) 4-warp teams, [b2,b1) 2-warp teams,
+    // [b1,bend) one warp per row
+    int b8, b4, b2, b1, bend;
+    // cumulative slot counts (a slot = one thread block's worth of rows)
+    int s8, s4, s2, n_slots;
+    int cap;   // resident entries per warp
+};
+
+template <typename T, int C, int L> struct ResidentSmem {
+    typedef Layout<T, C, L> Lay;
+    static constexpr int RED_STRIDE = Lay::KP + 4;
+    static constexpr int STRIPE = 2 * RED_STRIDE + Lay::KP;   // scratch per warp; a team of TW warps owns TW stripes
+};
+
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW>
+__device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, size_t beg, int nnz, T *stripes, const T *gram,
+                                             T *region, int cap, int w)
+{
+    typedef ResidentGather<T, C, L, TW == 8 || TW == 1> Gat;   // 2- and 4-warp teams only get rows that fit
+    const int team = w / TW, wt = w % TW;
+    // one named barrier per (team size, team): a block's teams run ahead of each other by whole slots
+    const int bar_id = (TW == 8) ? 1 : (TW == 4) ? 2 + team : (TW == 2) ? 4 + team : 0;
+    CgRow<T, C, L, MODEL, TW, GRAM_SMEM> s(p, stripes + (size_t)(team * TW) * ResidentSmem<T, C, L>::STRIPE, gram, wt, bar_id);
+    if (nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows)) {
+        Gat gat(p, region, cap, wt, TW);
+        gat.begin(beg, nnz);
+        gat.stage();
+        s.solve(row, nnz, gat);
+    } else {
+        s.empty_row(row);
+    }
+    team_barrier<TW>(bar_id);   // nobody of the team reuses scratch or regions before everybody is done with the row
+}
+
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM>
+__global__ void __launch_bounds__(kW * 32, 2) cg_resident_kernel(const CgSweepParams p, const ResidentPlan rp)
+{
+    typedef Layout<T, C, L> Lay;
+    typedef ResidentGather<T, C, L> Gat;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *stripes = reinterpret_cast<T *>(smem_raw);
+    T *gram_sm = stripes + kW * ResidentSmem<T, C, L>::STRIPE;
+    T *regions = gram_sm;
+    const T *gram = p.gram;
+    if constexpr (MODEL != kModelExplicit && GRAM_SMEM) {
+        const int kk = p.kk;
+        for (int i = threadIdx.x; i < kk * Lay::KP; i += blockDim.x) {
+            const int d = i / Lay::KP, c = i % Lay::KP;
+            gram_sm[i] = (c < kk) ? p.gram[(size_t)d * kk + c] : T(0);
+        }
+        gram = gram_sm;
+        regions = gram_sm + (size_t)kk * Lay::KP;
+        __syncthreads();
+    }
+    const int w = threadIdx.x >> 5;
+    T *region = regions + (size_t)w * rp.cap * (Gat::RS + 1);
+    Gat(p, region, rp.cap, 0, 1).clear_region();
+
+    // order-list position of the row this warp works on in a slot (-1: none)
+    auto decode = [&](int slot) -> int {
+        if (slot >= rp.n_slots) return -1;
+        if (slot < rp.s8) return rp.b8 + slot;
+        if (slot < rp.s4) {
+            const int ri = rp.b4 + (slot - rp.s8) * 2 + (w >> 2);
+            return ri < rp.b2 ? ri : -1;
+        }
+        if (slot < rp.s2) {
+            const int ri = rp.b2 + (slot - rp.s4) * 4 + (w >> 1);
+            return ri < rp.b1 ? ri : -1;
+        }
+        const int ri = rp.b1 + (slot - rp.s2) * 8 + w;
+        return ri < rp.bend ? ri : -1;
+    };
+    // the row id is fetched two slots ahead and its extent one slot ahead, so that neither load is waited for
+    const int step = gridDim.x;
+    int slot = blockIdx.x;
+    int ri = decode(slot);
+    int row0 = ri >= 0 ? p.plan.order[ri] : -1;
+    ri = decode(slot + step);
+    int row1 = ri >= 0 ? p.plan.order[ri] : -1;
+    size_t beg0 = 0, end0 = 0;
+    if (row0 >= 0) {
+        beg0 = p.X.ptr[row0];
+        end0 = p.X.ptr[row0 + 1];
+    }
+    for (; slot < rp.n_slots; slot += step) {
+        ri = decode(slot + 2 * step);
+        const int row2 = ri >= 0 ? p.plan.order[ri] : -1;
+        size_t beg1 = 0, end1 = 0;
+        if (row1 >= 0) {
+            beg1 = p.X.ptr[row1];
+            end1 = p.X.ptr[row1 + 1];
+        }
+        if (row0 >= 0) {
+            const int nnz = (int)(end0 - beg0);
+            if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+            else if (slot < rp.s4) resident_row<T, C, L, MODEL, GRAM_SMEM, 4>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+            else if (slot < rp.s2) resident_row<T, C, L, MODEL, GRAM_SMEM, 2>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+            else resident_row<T, C, L, MODEL, GRAM_SMEM, 1>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+        }
+        row0 = row1;
+        beg0 = beg1;
+        end0 = end1;
+        row1 = row2;
+    }
+}
+
+// rows [first, first + count) of the degree-sorted list, one row per cluster of CL thread blocks
+template <typename T, int C, int L, int MODEL, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kW * 32, 2)
+    cg_resident_cluster_kernel(const CgSweepParams p, int first, int count, int cap)
+{
+    namespace cg = cooperative_groups;
+    typedef TeamScratch<T, C, L, kW> Scr;
+    typedef ResidentGather<T, C, L> Gat;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *scratch = reinterpret_cast<T *>(smem_raw);
+    T *cl_buf = scratch + Scr::elems();                     // [2][RED_STRIDE]
+    T *regions = cl_buf + 2 * Scr::RED_STRIDE;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int w = threadIdx.x >> 5;
+    T *region = regions + (size_t)w * cap * (Gat::RS + 1);
+    Gat(p, region, cap, 0, 1).clear_region();
+    const int n_clusters = gridDim.x / CL;
+    int slot = blockIdx.x / CL;
+    int row0 = slot < count ? p.plan.order[first + slot] : -1;
+    int row1 = slot + n_clusters < count ? p.plan.order[first + slot + n_clusters] : -1;
+    size_t beg0 = 0, end0 = 0;
+    if (row0 >= 0) {
+        beg0 = p.X.ptr[row0];
+        end0 = p.X.ptr[row0 + 1];
+    }
+    for (; slot < count; slot += n_clusters) {
+        const int row2 = slot + 2 * n_clusters < count ? p.plan.order[first + slot + 2 * n_clusters] : -1;
+        size_t beg1 = 0, end1 = 0;
+        if (row1 >= 0) {
+            beg1 = p.X.ptr[row1];
+            end1 = p.X.ptr[row1 + 1];
+        }
+        const int nnz = (int)(end0 - beg0);
+        CgRow<T, C, L, MODEL, kW, false, CL> s(p, scratch, p.gram, w, 0);
+        s.cl_buf = cl_buf;
+        s.cl_rank = rank;   // only block 0 of the cluster writes the row back
+        Gat gat(p, region, cap, rank * kW + w, CL * kW);
+        gat.begin(beg0, nnz);
+        gat.stage();
+        s.solve(row0, nnz, gat);
+        cluster.sync();
+        row0 = row1;
+        beg0 = beg1;
+        end0 = end1;
+        row1 = row2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+int env_int(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+struct SideStreams {
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    bool ok = false;
+    SideStreams()
+    {
+        ok = true;
+        for (int i = 0; i < 3; i++) {
+            ok = ok && cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        ok = ok && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess;
+    }
+};
+
+SideStreams &side_streams()
+{
+    static SideStreams ss;   // one process drives one GPU
+    return ss;
+}
+
+// number of rows of the (descending) degree list with more than `x` stored entries
+int count_gt(const int_t *deg, int n, long long x)
+{
+    return (int)(std::lower_bound(deg, deg + n, x, [](int_t d, long long v) { return (long long)d > v; }) - deg);
+}
+
+template <typename T, int C, int L, int MODEL, int CL>
+int launch_cluster(const CgSweepParams &p, int first, int count, int cap, size_t smem, cudaStream_t stream)
+{
+    auto kern = cg_resident_cluster_kernel<T, C, L, MODEL, CL>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 1, 1);
+    cfg.blockDim = dim3(kW * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    const int clusters = count < max_clusters ? count : max_clusters;
+    kern<<<clusters * CL, kW * 32, smem, stream>>>(p, first, count, cap);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+template <typename T, int C, int L, int MODEL>
+int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+{
+    typedef Layout<T, C, L> Lay;
+    typedef ResidentGather<T, C, L> Gat;
+    typedef ResidentSmem<T, C, L> SM;
+    typedef TeamScratch<T, C, L, kW> Scr;
+    const int n_rows = p.plan.n_rows;
+    const int_t *deg = p.plan.host_deg;
+    if (!deg) return 3;
+    if (n_rows <= 0) return 0;
+
+    int dev = 0, sms = 148, smem_sm = 233472, smem_optin = 232448;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // thread blocks per SM (default two); the driver reserves 1 KB per block
+    const int bps = env_int("CMFB200_RES_BPS", 2) == 1 ? 1 : 2;
+    size_t per_block = (size_t)smem_sm / bps - 1024;
+    if (per_block > (size_t)smem_optin) per_block = (size_t)smem_optin;
+
+    const size_t fixed1 = (size_t)kW * SM::STRIPE * sizeof(T);
+    size_t gram_bytes = MODEL != kModelExplicit ? (size_t)p.kk * Lay::KP * sizeof(T) : 0;
+    const bool gram_smem = MODEL != kModelExplicit && gram_bytes <= per_block / 3;
+    if (!gram_smem) gram_bytes = 0;
+    if (fixed1 + gram_bytes >= per_block) return 3;
+    const int cap1 = (int)((per_block - fixed1 - gram_bytes) / (kW * Gat::kEntryBytes)) & ~7;
+    const size_t fixedC = (size_t)(Scr::elems() + 2 * Scr::RED_STRIDE) * sizeof(T);
+    const int capC = (int)((per_block - fixedC) / (kW * Gat::kEntryBytes)) & ~7;
+    if (cap1 < 8 || capC < 8) return 3;   // rows too wide for shared-memory residency: use the direct kernel
+
+    // buckets of the degree-sorted row list, largest rows first
+    const int pct8 = env_int("CMFB200_RES_OVF8", 100);   // % of an 8-warp team's capacity a block-level row may have
+    const bool use_clusters = env_int("CMFB200_RES_CLUSTERS", 1) != 0;
+    const long long cap_block = (long long)kW * cap1 * pct8 / 100;
+    int nC8 = 0, nC4 = 0, nC2 = 0;
+    if (use_clusters) {
+        nC8 = count_gt(deg, n_rows, (long long)4 * kW * capC);
+        nC4 = count_gt(deg, n_rows, (long long)2 * kW * capC);
+        nC2 = count_gt(deg, n_rows, cap_block);
+        if (nC4 < nC8) nC4 = nC8;
+        if (nC2 < nC4) nC2 = nC4;
+    }
+    ResidentPlan rp;
+    rp.cap = cap1;
+    // mode 1 (default, measured fastest): one warp per row with a shared-memory cache; mode 0: teams sized so that
+    // whole rows are resident (1-8 warps, clusters of 2-8 blocks) -- fewer L2 reads but the per-pass team overhead
+    // costs more instructions than the gathers it saves (profiles/README.md)
+    const int mode = env_int("CMFB200_RES_MODE", 1);
+    if (mode == 1 && cap1 < 32) return 3;   // wide rows: the cache holds too little to pay for the staging
+    if (mode == 1) {
+        // one warp per row as in the direct kernel, the first cap1 entries of every row resident, the rest streamed;
+        // rows of >= 1024 entries get a thread block, rows of >= 8192 a cluster of 8
+        nC8 = use_clusters ? count_gt(deg, n_rows, 8191) : 0;
+        nC4 = nC2 = nC8;
+        rp.b8 = nC8;
+        rp.b4 = rp.b2 = rp.b1 = std::max(rp.b8, count_gt(deg, n_rows, 1023));
+    } else {
+        rp.b8 = nC2;
+        rp.b4 = std::max(rp.b8, count_gt(deg, n_rows, (long long)4 * cap1));
+        rp.b2 = std::max(rp.b4, count_gt(deg, n_rows, (long long)2 * cap1));
+        rp.b1 = std::max(rp.b2, count_gt(deg, n_rows, (long long)cap1));
+    }
+    rp.bend = n_rows;
+    rp.s8 = rp.b4 - rp.b8;
+    rp.s4 = rp.s8 + (rp.b2 - rp.b4 + 1) / 2;
+    rp.s2 = rp.s4 + (rp.b1 - rp.b2 + 3) / 4;
+    rp.n_slots = rp.s2 + (rp.bend - rp.b1 + 7) / 8;
+
+    SideStreams &ss = side_streams();
+    if (!ss.ok) return 1;
+    const size_t smemC = fixedC + (size_t)kW * capC * Gat::kEntryBytes;
+    const int cl_first[3] = {0, nC8, nC4}, cl_count[3] = {nC8, nC4 - nC8, nC2 - nC4};
+    bool forked = false;
+    for (int i = 0; i < 3; i++) {
+        if (cl_count[i] <= 0) continue;
+        if (!forked) {
+            cudaEventRecord(ss.fork, stream);
+            forked = true;
+        }
+        cudaStreamWaitEvent(ss.s[i], ss.fork, 0);
+        int rc;
+        if (i == 0) rc = launch_cluster<T, C, L, MODEL, 8>(p, cl_first[i], cl_count[i], capC, smemC, ss.s[i]);
+        else if (i == 1) rc = launch_cluster<T, C, L, MODEL, 4>(p, cl_first[i], cl_count[i], capC, smemC, ss.s[i]);
+        else rc = launch_cluster<T, C, L, MODEL, 2>(p, cl_first[i], cl_count[i], capC, smemC, ss.s[i]);
+        if (rc) return rc;
+        cudaEventRecord(ss.join[i], ss.s[i]);
+        if (n_launches) (*n_launches)++;
+    }
+    if (rp.n_slots > 0) {
+        const size_t smem1 = fixed1 + gram_bytes + (size_t)kW * cap1 * Gat::kEntryBytes;
+        auto kern = gram_smem ? cg_resident_kernel<T, C, L, MODEL, true> : cg_resident_kernel<T, C, L, MODEL, false>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess) return 1;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kW * 32, smem1);
+        if (occ < 1) return 1;
+        long long grid = (long long)sms * occ;
+        if (grid > rp.n_slots) grid = rp.n_slots;
+        kern<<<(unsigned)grid, kW * 32, smem1, stream>>>(p, rp);
+        if (cudaGetLastError() != cudaSuccess) return 1;
+        if (n_launches) (*n_launches)++;
+    }
+    for (int i = 0; i < 3; i++)
+        if (cl_count[i] > 0) cudaStreamWaitEvent(stream, ss.join[i], 0);
+    return 0;
+}
+
+template <int MODEL> int dispatch_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+{
+    const int kk = p.kk;
+    if (kk < 1) return 2;
+#ifdef USE_FLOAT
+    if (kk <= 16) return launch_resident_cfg<float, 4, 4, MODEL>(p, stream, n_launches);
+    if (kk <= 32) return launch_resident_cfg<float, 8, 4, MODEL>(p, stream, n_launches);
+    if (kk <= 64) return launch_resident_cfg<float, 16, 4, MODEL>(p, stream, n_launches);
+    if (kk <= 128) return launch_resident_cfg<float, 8, 16, MODEL>(p, stream, n_launches);
+    if (kk <= 256) return launch_resident_cfg<float, 8, 32, MODEL>(p, stream, n_launches);
+#else
+    if (kk <= 16) return launch_resident_cfg<double, 4, 4, MODEL>(p, stream, n_launches);
+    if (kk <= 32) return launch_resident_cfg<double, 4, 8, MODEL>(p, stream, n_launches);
+    if (kk <= 64) return launch_resident_cfg<double, 4, 16, MODEL>(p, stream, n_launches);
+    if (kk <= 128) return launch_resident_cfg<double, 4, 32, MODEL>(p, stream, n_launches);
+#endif
+    return 3;
+}
+
+}  // namespace
+
+// 0 = launched, 3 = this shape is not covered (nothing was launched: use the direct kernel), other = error
+int launch_explicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+{
+    return (p.gram || p.qvec || p.solve_all_rows) ? dispatch_resident<kModelCollective>(p, stream, n_launches)
+                                                  : dispatch_resident<kModelExplicit>(p, stream, n_launches);
+}
+int launch_implicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+{
+    return dispatch_resident<kModelImplicit>(p, stream, n_launches);
+}
+
+}  // namespace cmfb200
