@@ -423,8 +423,14 @@ int AlsState::half_sweep(int which, int iter, int solver)
     }
     if (solver == 0) {
         rc = 3;
-        // default: rows resident in shared memory across the CG passes (sweep_cg_resident.cu)
-        if (env_or("CMFB200_RESIDENT", 1)) {
+        // default: panels resident in shared memory across the CG passes (sweep_cg_panel.cu)
+        if (env_or("CMFB200_PANEL", 1)) {
+            int nl = 0;
+            rc = cfg.implicit ? launch_implicit_cg_sweep_panel(p, stream, &nl) : launch_explicit_cg_sweep_panel(p, stream, &nl);
+            if (rc == 0) launches += nl - 1;
+        }
+        // earlier variant of the same idea (sweep_cg_resident.cu)
+        if (rc == 3 && env_or("CMFB200_RESIDENT", 1)) {
             int nl = 0;
             rc = cfg.implicit ? launch_implicit_cg_sweep_resident(p, stream, &nl) : launch_explicit_cg_sweep_resident(p, stream, &nl);
             if (rc == 0) launches += nl - 1;

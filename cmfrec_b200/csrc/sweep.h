@@ -62,6 +62,12 @@ int launch_implicit_cg_sweep_staged(const CgSweepParams &p, cudaStream_t stream)
 int launch_explicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
 int launch_implicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
 
+// Panel variant (sweep_cg_panel.cu): the gathered rows resident in shared memory, predicate-free pipelined passes,
+// transposed reductions, distributed CG algebra, run-time team sizes, clusters of 2-16 thread blocks for long rows.
+// Return 3 when the shape is not covered.
+int launch_explicit_cg_sweep_panel(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
+int launch_implicit_cg_sweep_panel(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
+
 // Exact per-row solves (normal equations + Cholesky); same parameter block, `max_cg_steps` and
 // `bias_start_one` only matter for rows without entries.  reference: factors_closed_form sparse branch
 // src/common.c:978-1013 + 1058-1070, factors_implicit_chol src/common.c:2063-2126.
