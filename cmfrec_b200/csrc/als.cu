@@ -423,13 +423,15 @@ int AlsState::half_sweep(int which, int iter, int solver)
     }
     if (solver == 0) {
         rc = 3;
-        // default: panels resident in shared memory across the CG passes (sweep_cg_panel.cu)
-        if (env_or("CMFB200_PANEL", 1)) {
+        // opt-in: whole rows resident in shared memory across the CG passes, teams and clusters (sweep_cg_panel.cu);
+        // parity-green but slower than the cached kernel below on the measured shapes (profiles/README.md)
+        if (env_or("CMFB200_PANEL", 0)) {
             int nl = 0;
             rc = cfg.implicit ? launch_implicit_cg_sweep_panel(p, stream, &nl) : launch_explicit_cg_sweep_panel(p, stream, &nl);
             if (rc == 0) launches += nl - 1;
         }
-        // earlier variant of the same idea (sweep_cg_resident.cu)
+        // default: one warp per row (a thread block / a cluster of 8 for long rows), the first entries of every share
+        // cached in shared memory, the rest streamed through a pipelined gather (sweep_cg_resident.cu)
         if (rc == 3 && env_or("CMFB200_RESIDENT", 1)) {
             int nl = 0;
             rc = cfg.implicit ? launch_implicit_cg_sweep_resident(p, stream, &nl) : launch_explicit_cg_sweep_resident(p, stream, &nl);

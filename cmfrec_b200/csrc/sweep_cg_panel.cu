@@ -166,13 +166,27 @@ template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int CL> struct Pa
                 xs[2 * e] = x;
                 xs[2 * e + 1] = T(1);
             }
+            if constexpr (P::U <= 32) {
+                // 32 / U entries per round: lane -> (entry lane / U of the round, piece lane % U)
+                constexpr int EPR = 32 / P::U;
+                const int part = lane % P::U;
+                const bool in_row = part * VN < ldG;
+                T *dst = rows + (size_t)(i * 32 + lane / P::U) * RS + part * VN;
+                const T *src = p.G + part * VN;
 #pragma unroll 4
-            for (int j = 0; j < P::U; j++) {
-                const int u = j * 32 + lane;
-                const int ent = u / P::U, part = u % P::U;
-                const int c = __shfl_sync(CMF_FULL_MASK, col, ent);
-                if (c >= 0 && part * VN < ldG)
-                    panel_cp_async_16(rows + (size_t)(i * 32 + ent) * RS + part * VN, p.G + (size_t)c * (size_t)ldG + part * VN);
+                for (int j = 0; j < P::U; j++) {
+                    const int c = __shfl_sync(CMF_FULL_MASK, col, j * EPR + lane / P::U);
+                    if (c >= 0 && in_row) panel_cp_async_16(dst + (size_t)(j * EPR) * RS, src + (size_t)c * (size_t)ldG);
+                }
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < P::U; j++) {
+                    const int u = j * 32 + lane;
+                    const int ent = u / P::U, part = u % P::U;
+                    const int c = __shfl_sync(CMF_FULL_MASK, col, ent);
+                    if (c >= 0 && part * VN < ldG)
+                        panel_cp_async_16(rows + (size_t)(i * 32 + ent) * RS + part * VN, p.G + (size_t)c * (size_t)ldG + part * VN);
+                }
             }
         }
         // padding up to whole steps: zero rows, zero value, zero "one"
@@ -226,14 +240,19 @@ template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int CL> struct Pa
         T v0[C], v1[C], x0, x1, o0, o1;
         load_step(0, v0, x0, o0);
         int s = 0;
-        for (; s + 1 < nsteps; s += 2) {
+        for (; s + 2 < nsteps; s += 2) {
             load_step(s + 1, v1, x1, o1);
             step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
-            const int nx = s + 2 < nsteps ? s + 2 : nsteps - 1;
-            load_step(nx, v0, x0, o0);
+            load_step(s + 2, v0, x0, o0);
             step<KIND>(v1, x1, o1, vec, vecb, acc, accb);
         }
-        if (s < nsteps) step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
+        if (s + 1 < nsteps) {
+            load_step(s + 1, v1, x1, o1);
+            step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
+            step<KIND>(v1, x1, o1, vec, vecb, acc, accb);
+        } else {
+            step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
+        }
     }
 
     // acc += sign * gram * vec; the rows of gram are dealt over all groups of the team; vec is read from the warp's
@@ -798,14 +817,21 @@ int launch_panel_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_launche
         pd.plan.n_rows = n_direct;
         pd.plan.n_long = std::min<int_t>(p.plan.n_long, n_direct);
         pd.plan.n_huge = std::min<int_t>(p.plan.n_huge, n_direct);
-        pd.plan.host_deg = nullptr;
         pd.side_stream = nullptr;
         fork_to(4);
-        const int rc = MODEL == kModelImplicit ? launch_implicit_cg_sweep(pd, ss.s[4]) : launch_explicit_cg_sweep(pd, ss.s[4]);
+        // the cached kernel (first entries of every share resident, the rest streamed) where it covers the shape,
+        // else the direct kernel
+        int nl = 0;
+        int rc = MODEL == kModelImplicit ? launch_implicit_cg_sweep_resident(pd, ss.s[4], &nl) : launch_explicit_cg_sweep_resident(pd, ss.s[4], &nl);
+        if (rc == 3) {
+            pd.plan.host_deg = nullptr;
+            rc = MODEL == kModelImplicit ? launch_implicit_cg_sweep(pd, ss.s[4]) : launch_explicit_cg_sweep(pd, ss.s[4]);
+            nl = pd.plan.n_huge > 0 ? 2 : 1;
+        }
         if (rc) return rc;
         cudaEventRecord(ss.join[4], ss.s[4]);
         used[4] = true;
-        if (n_launches) (*n_launches) += pd.plan.n_huge > 0 ? 2 : 1;
+        if (n_launches) (*n_launches) += nl;
     }
     for (int i = 0; i < 4; i++) {
         const int cfirst = bounds[i], ccount = bounds[i + 1] - bounds[i];

@@ -54,11 +54,14 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     static constexpr int PAD = (L == 4) ? VN : 0;
     static constexpr int RS = KP + PAD;        // elements between staged rows
     static constexpr int U = KP / VN;          // 16-byte pieces per staged row
-    static constexpr size_t kEntryBytes = (size_t)(RS + 1) * sizeof(T);   // staged row + staged value
+    // staged row + {stored value, "one"}: the resident part of a share is padded to whole steps of G entries with
+    // zero rows whose value and "one" are zero, which makes every form of the per-entry coefficient vanish there,
+    // so the pass over the resident part carries no predicates at all
+    static constexpr size_t kEntryBytes = (size_t)(RS + 2) * sizeof(T);
 
     const CgSweepParams &p;
     T *rows;          // [cap][RS]
-    T *xs;            // [cap]   stored value, already reduced by the opposing bias (explicit model)
+    T *xs;            // [cap][2]   stored value (explicit model: already reduced by the opposing bias), 1.0
     int cap;          // resident entries of this warp (multiple of 8)
     size_t beg;       // first entry of this warp's share of the row
     int nnz;          // entries in this warp's share
@@ -92,32 +95,46 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     {
         __syncwarp();
         const int ldG = p.ldG;
-        for (int i = 0; i * 32 < nnz && i * 32 < cap; i++) {
+        const int res = nnz < cap ? nnz : cap;
+        for (int i = 0; i * 32 < res; i++) {
             const int e = i * 32 + lane;
-            const int slot = e;
             int col = -1;
-            if (e < nnz && slot < cap) {
+            if (e < res) {
                 col = p.X.idx[beg + e];
                 T x = p.X.val[beg + e];
                 if (p.center_opp) x -= __ldg(p.Gbias + col);
-                xs[slot] = x;
+                xs[2 * e] = x;
+                xs[2 * e + 1] = T(1);
             }
+            if constexpr (U <= 32) {
+                // 32 / U entries per round: lane -> (entry lane / U of the round, piece lane % U)
+                constexpr int EPR = 32 / U;
+                const int part = lane % U;
+                const bool in_row = part * VN < ldG;
+                T *dst = rows + (size_t)(i * 32 + lane / U) * RS + part * VN;
+                const T *src = p.G + part * VN;
 #pragma unroll 4
-            for (int j = 0; j < U; j++) {
-                const int u = j * 32 + lane;
-                const int ent = u / U, part = u % U;
-                const int c = __shfl_sync(CMF_FULL_MASK, col, ent);
-                if (c >= 0 && part * VN < ldG)
-                    cp_async_16(rows + (size_t)(i * 32 + ent) * RS + part * VN, p.G + (size_t)c * (size_t)ldG + part * VN);
+                for (int j = 0; j < U; j++) {
+                    const int c = __shfl_sync(CMF_FULL_MASK, col, j * EPR + lane / U);
+                    if (c >= 0 && in_row) cp_async_16(dst + (size_t)(j * EPR) * RS, src + (size_t)c * (size_t)ldG);
+                }
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < U; j++) {
+                    const int u = j * 32 + lane;
+                    const int ent = u / U, part = u % U;
+                    const int c = __shfl_sync(CMF_FULL_MASK, col, ent);
+                    if (c >= 0 && part * VN < ldG)
+                        cp_async_16(rows + (size_t)(i * 32 + ent) * RS + part * VN, p.G + (size_t)c * (size_t)ldG + part * VN);
+                }
             }
         }
-        // slots between the share's last entry and the end of its last group of G are read by the passes: zero them
+        // padding of the resident part up to whole steps of G entries: zero rows, zero value, zero "one"
         // (everything else a pass reads was either staged above or zeroed when the kernel started)
         {
-            const int res = nnz < cap ? nnz : cap;
             const int tail_end = (res + G - 1) / G * G;
             for (int u = res * RS + lane; u < tail_end * RS; u += 32) rows[u] = T(0);
-            if (res + lane < tail_end) xs[res + lane] = T(0);
+            for (int u = 2 * res + lane; u < 2 * tail_end; u += 32) xs[u] = T(0);
         }
         cp_async_commit_wait_all();
         __syncwarp();
@@ -126,60 +143,137 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     // once per kernel: columns the staging never writes (>= ldG) must read as zero
     __device__ __forceinline__ void clear_region()
     {
-        for (int u = lane; u < cap * (RS + 1); u += 32) rows[u] = T(0);
+        for (int u = lane; u < cap * (RS + 2); u += 32) rows[u] = T(0);
         __syncwarp();
+    }
+
+    // ---- one step = G entries, one per group
+    __device__ __forceinline__ void load_resident(int s, T (&v)[C], T &x, T &one) const
+    {
+        const int slot = s * G + gi;
+        const T *srow = rows + (size_t)slot * RS;
+#pragma unroll
+        for (int q = 0; q < C / VN; q++) {
+            const Vec vv = *reinterpret_cast<const Vec *>(srow + (q * L + l) * VN);
+            const T *pv = reinterpret_cast<const T *>(&vv);
+#pragma unroll
+            for (int e2 = 0; e2 < VN; e2++) v[q * VN + e2] = pv[e2];
+        }
+        x = xs[2 * slot];
+        one = xs[2 * slot + 1];
+    }
+
+    // entry `ent` of a 32-entry chunk whose (column, value) pairs sit one per lane; FULLW: the opposing rows are at
+    // least KP wide, so that no piece needs a bounds check
+    template <bool FULLW>
+    __device__ __forceinline__ void load_streamed(int col_r, T x_r, int ent, T (&v)[C], T &x, T &one) const
+    {
+        const int col = __shfl_sync(CMF_FULL_MASK, col_r, ent);
+        x = __shfl_sync(CMF_FULL_MASK, x_r, ent);
+        const bool ok = col >= 0;
+        one = ok ? T(1) : T(0);
+        const T *grow = p.G + (size_t)(ok ? col : 0) * (size_t)p.ldG + l * VN;
+#pragma unroll
+        for (int q = 0; q < C / VN; q++) {
+            if (FULLW || (q * L + l) * VN < p.ldG) {
+                ldg_vec(grow + q * L * VN, &v[q * VN]);
+            } else {
+#pragma unroll
+                for (int e2 = 0; e2 < VN; e2++) v[q * VN + e2] = T(0);
+            }
+        }
+    }
+
+    template <int KIND>
+    __device__ __forceinline__ void step(const T (&v)[C], T x, T one, const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
+    {
+        T d = group_sum<L>(dot_pairs<C>(v, vec));
+        d = fma(vecb, one, d);   // opposing value of the bias coordinate is 1 (vecb is 0 when there is none)
+        T coef = entry_coef<KIND>(d, x);
+        if (one == T(0)) coef = T(0);   // padding / past the end of a streamed chunk
+        axpy_pairs<C>(coef, v, acc);
+        accb += coef;
+    }
+
+    // (column, value) of entry e0 + lane of this warp's share, -1 / 0 past its end
+    template <int KIND> __device__ __forceinline__ void load_chunk(int e0, int &col_r, T &x_r) const
+    {
+        const int e = e0 + lane;
+        col_r = -1;
+        x_r = T(0);
+        if (e < nnz) {
+            col_r = p.X.idx[beg + e];
+            x_r = p.X.val[beg + e];
+            if (KIND == kExplicitResidual && p.center_opp) x_r -= __ldg(p.Gbias + col_r);
+        }
+    }
+
+    // Entries beyond the resident part, 32 at a time.  The gathers run D steps ahead of the arithmetic (D rotating
+    // register buffers, no load issued twice) and the (column, value) pairs of the next chunk are fetched while the
+    // current one is processed: the streamed part is bound by L2 latency, i.e. by the bytes in flight per warp.
+    static constexpr int D = (C <= 8 && L >= 4) ? 4 : 2;
+    template <int KIND, bool FULLW>
+    __device__ __forceinline__ void pass_streamed(const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
+    {
+        int col_r, col_n = -1;
+        T x_r, x_n = T(0);
+        load_chunk<KIND>(cap, col_r, x_r);
+        for (int e0 = cap; e0 < nnz; e0 += 32) {
+            if (e0 + 32 < nnz) load_chunk<KIND>(e0 + 32, col_n, x_n);
+            const int left = nnz - e0;
+            if (left >= 32) {
+                // full chunk: L steps in a straight line, every buffer index a compile-time constant
+                T v[D][C], x[D], o[D];
+#pragma unroll
+                for (int d = 0; d < D - 1; d++) load_streamed<FULLW>(col_r, x_r, d * G + gi, v[d], x[d], o[d]);
+#pragma unroll
+                for (int t = 0; t < L; t++) {
+                    if (t + D - 1 < L)
+                        load_streamed<FULLW>(col_r, x_r, (t + D - 1) * G + gi, v[(t + D - 1) % D], x[(t + D - 1) % D], o[(t + D - 1) % D]);
+                    step<KIND>(v[t % D], x[t % D], o[t % D], vec, vecb, acc, accb);
+                }
+            } else {
+                // last, partial chunk of the share
+                const int nst = (left + G - 1) / G;
+                for (int t = 0; t < nst; t++) {
+                    T v[C], x, o;
+                    load_streamed<FULLW>(col_r, x_r, t * G + gi, v, x, o);
+                    step<KIND>(v, x, o, vec, vecb, acc, accb);
+                }
+            }
+            col_r = col_n;
+            x_r = x_n;
+        }
     }
 
     template <int KIND>
     __device__ __forceinline__ void pass(const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
     {
-        const int ldG = p.ldG;
-        for (int i = 0; i * 32 < nnz; i++) {
-            const int li0 = i * 32;
-            const int left = nnz - li0;       // entries from this chunk on (may exceed 32)
-            int col_r = -1;
-            T x_r = T(0);
-            if constexpr (STREAM) {
-                if (li0 + 32 > cap) {         // warp-uniform: part of the chunk is not resident
-                    const int e = li0 + lane;
-                    if (e < nnz) {
-                        col_r = p.X.idx[beg + e];
-                        x_r = p.X.val[beg + e];
-                    }
-                }
+        // resident part: software-pipelined two steps deep, no predicates
+        const int res = nnz < cap ? nnz : cap;
+        const int nsteps = (res + G - 1) / G;
+        if (nsteps > 0) {
+            T v0[C], v1[C], x0, x1, o0, o1;
+            load_resident(0, v0, x0, o0);
+            int s = 0;
+            for (; s + 2 < nsteps; s += 2) {
+                load_resident(s + 1, v1, x1, o1);
+                step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
+                load_resident(s + 2, v0, x0, o0);
+                step<KIND>(v1, x1, o1, vec, vecb, acc, accb);
             }
-#pragma unroll 4
-            for (int t = 0; t < L; t++) {
-                if (t * G >= left) break;     // warp-uniform
-                const int ent = t * G + gi;
-                const bool valid = ent < left;
-                T v[C];
-                T x = T(0);
-                if (!STREAM || li0 + t * G < cap) {   // warp-uniform: these G entries are resident
-                    const int slot = li0 + ent;
-                    const T *srow = rows + (size_t)slot * RS;
-#pragma unroll
-                    for (int q = 0; q < C / VN; q++) {
-                        const Vec vv = *reinterpret_cast<const Vec *>(srow + (q * L + l) * VN);
-                        const T *pv = reinterpret_cast<const T *>(&vv);
-#pragma unroll
-                        for (int e2 = 0; e2 < VN; e2++) v[q * VN + e2] = pv[e2];
-                    }
-                    x = xs[slot];
-                } else if constexpr (STREAM) {
-                    const int col = __shfl_sync(CMF_FULL_MASK, col_r, ent);
-                    x = __shfl_sync(CMF_FULL_MASK, x_r, ent);
-                    const bool ok = col >= 0;
-                    const T *grow = p.G + (size_t)(ok ? col : 0) * (size_t)ldG;
-                    gather_row<T, C, L>(grow, l, ldG, ok, v);
-                    if (KIND == kExplicitResidual && p.center_opp && ok) x -= __ldg(p.Gbias + col);
-                }
-                T d = group_sum<L>(dot_pairs<C>(v, vec));
-                d += vecb;   // opposing value of the bias coordinate is 1 (vecb is 0 when there is none)
-                T coef = entry_coef<KIND>(d, x);
-                if (!valid) coef = T(0);
-                axpy_pairs<C>(coef, v, acc);
-                accb += coef;
+            if (s + 1 < nsteps) {
+                load_resident(s + 1, v1, x1, o1);
+                step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
+                step<KIND>(v1, x1, o1, vec, vecb, acc, accb);
+            } else {
+                step<KIND>(v0, x0, o0, vec, vecb, acc, accb);
+            }
+        }
+        if constexpr (STREAM) {
+            if (nnz > cap) {   // warp-uniform
+                if (p.ldG >= KP) pass_streamed<KIND, true>(vec, vecb, acc, accb);
+                else pass_streamed<KIND, false>(vec, vecb, acc, accb);
             }
         }
     }
@@ -223,8 +317,8 @@ __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, si
     team_barrier<TW>(bar_id);   // nobody of the team reuses scratch or regions before everybody is done with the row
 }
 
-template <typename T, int C, int L, int MODEL, bool GRAM_SMEM>
-__global__ void __launch_bounds__(kW * 32, 2) cg_resident_kernel(const CgSweepParams p, const ResidentPlan rp)
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int MINB = 2>
+__global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSweepParams p, const ResidentPlan rp)
 {
     typedef Layout<T, C, L> Lay;
     typedef ResidentGather<T, C, L> Gat;
@@ -244,7 +338,7 @@ __global__ void __launch_bounds__(kW * 32, 2) cg_resident_kernel(const CgSweepPa
         __syncthreads();
     }
     const int w = threadIdx.x >> 5;
-    T *region = regions + (size_t)w * rp.cap * (Gat::RS + 1);
+    T *region = regions + (size_t)w * rp.cap * (Gat::RS + 2);
     Gat(p, region, rp.cap, 0, 1).clear_region();
 
     // order-list position of the row this warp works on in a slot (-1: none)
@@ -311,7 +405,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kW * 32, 2)
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int w = threadIdx.x >> 5;
-    T *region = regions + (size_t)w * cap * (Gat::RS + 1);
+    T *region = regions + (size_t)w * cap * (Gat::RS + 2);
     Gat(p, region, cap, 0, 1).clear_region();
     const int n_clusters = gridDim.x / CL;
     int slot = blockIdx.x / CL;
@@ -408,7 +502,7 @@ int launch_cluster(const CgSweepParams &p, int first, int count, int cap, size_t
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-template <typename T, int C, int L, int MODEL>
+template <typename T, int C, int L, int MODEL, int MINB = 2>
 int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
 {
     typedef Layout<T, C, L> Lay;
@@ -426,19 +520,33 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     // thread blocks per SM (default two); the driver reserves 1 KB per block
-    const int bps = env_int("CMFB200_RES_BPS", 2) == 1 ? 1 : 2;
+    const int bps = env_int("CMFB200_RES_BPS", MINB) == 1 ? 1 : MINB;
     size_t per_block = (size_t)smem_sm / bps - 1024;
     if (per_block > (size_t)smem_optin) per_block = (size_t)smem_optin;
 
+    // mode 1 (default, measured fastest): one warp per row with a shared-memory cache; mode 0: teams sized so that
+    // whole rows are resident (1-8 warps, clusters of 2-8 blocks) -- fewer L2 reads but the per-pass team overhead
+    // costs more instructions than the gathers it saves (profiles/README.md)
+    const int mode = env_int("CMFB200_RES_MODE", 1);
     const size_t fixed1 = (size_t)kW * SM::STRIPE * sizeof(T);
     size_t gram_bytes = MODEL != kModelExplicit ? (size_t)p.kk * Lay::KP * sizeof(T) : 0;
-    const bool gram_smem = MODEL != kModelExplicit && gram_bytes <= per_block / 3;
+    // The constant matrix goes to shared memory whenever it fits (every row reads all of it on every pass); what is
+    // left is the cache of gathered rows.  In mode 1 the cache may be small or empty (wide rows): the rest of every
+    // share is streamed through the pipelined gather, and shared memory that is not asked for stays L1.
+    const bool gram_smem =
+        MODEL != kModelExplicit && (mode == 1 ? fixed1 + gram_bytes + 1024 <= per_block : gram_bytes <= per_block / 3);
     if (!gram_smem) gram_bytes = 0;
     if (fixed1 + gram_bytes >= per_block) return 3;
-    const int cap1 = (int)((per_block - fixed1 - gram_bytes) / (kW * Gat::kEntryBytes)) & ~7;
+    int cap1 = (int)((per_block - fixed1 - gram_bytes) / (kW * Gat::kEntryBytes)) & ~7;
     const size_t fixedC = (size_t)(Scr::elems() + 2 * Scr::RED_STRIDE) * sizeof(T);
-    const int capC = (int)((per_block - fixedC) / (kW * Gat::kEntryBytes)) & ~7;
-    if (cap1 < 8 || capC < 8) return 3;   // rows too wide for shared-memory residency: use the direct kernel
+    int capC = (int)((per_block - fixedC) / (kW * Gat::kEntryBytes)) & ~7;
+    if (mode != 1 && (cap1 < 8 || capC < 8)) return 3;   // teams need whole rows resident
+    if (mode == 1) {
+        // a cache of fewer than 16 entries per warp does not pay for its staging: stream everything, keep the L1
+        const int min_cap = env_int("CMFB200_RES_MINCAP", 16);
+        if (cap1 < min_cap) cap1 = 0;
+        if (capC < min_cap) capC = 0;
+    }
 
     // buckets of the degree-sorted row list, largest rows first
     const int pct8 = env_int("CMFB200_RES_OVF8", 100);   // % of an 8-warp team's capacity a block-level row may have
@@ -454,11 +562,6 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     }
     ResidentPlan rp;
     rp.cap = cap1;
-    // mode 1 (default, measured fastest): one warp per row with a shared-memory cache; mode 0: teams sized so that
-    // whole rows are resident (1-8 warps, clusters of 2-8 blocks) -- fewer L2 reads but the per-pass team overhead
-    // costs more instructions than the gathers it saves (profiles/README.md)
-    const int mode = env_int("CMFB200_RES_MODE", 1);
-    if (mode == 1 && cap1 < 32) return 3;   // wide rows: the cache holds too little to pay for the staging
     if (mode == 1) {
         // one warp per row as in the direct kernel, the first cap1 entries of every row resident, the rest streamed;
         // rows of >= 1024 entries get a thread block, rows of >= 8192 a cluster of 8
@@ -500,7 +603,7 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     }
     if (rp.n_slots > 0) {
         const size_t smem1 = fixed1 + gram_bytes + (size_t)kW * cap1 * Gat::kEntryBytes;
-        auto kern = gram_smem ? cg_resident_kernel<T, C, L, MODEL, true> : cg_resident_kernel<T, C, L, MODEL, false>;
+        auto kern = gram_smem ? cg_resident_kernel<T, C, L, MODEL, true, MINB> : cg_resident_kernel<T, C, L, MODEL, false, MINB>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess) return 1;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kW * 32, smem1);
@@ -523,7 +626,14 @@ template <int MODEL> int dispatch_resident(const CgSweepParams &p, cudaStream_t 
 #ifdef USE_FLOAT
     if (kk <= 16) return launch_resident_cfg<float, 4, 4, MODEL>(p, stream, n_launches);
     if (kk <= 32) return launch_resident_cfg<float, 8, 4, MODEL>(p, stream, n_launches);
-    if (kk <= 64) return launch_resident_cfg<float, 16, 4, MODEL>(p, stream, n_launches);
+    if (kk <= 64) {
+        // 8 lanes per entry read whole 128-byte lines (half the L1 wavefronts of the 4-lane layout on streamed gathers)
+        // (measured: 1.84 vs 1.87 ms / iteration at ML10M shape, 5.67 vs 7.13 ms at LastFM shape, profiles/README.md)
+        const int v = env_int("CMFB200_RES_CFG64", 1);
+        if (v == 0) return launch_resident_cfg<float, 16, 4, MODEL>(p, stream, n_launches);
+        if (v == 3) return launch_resident_cfg<float, 8, 8, MODEL, 3>(p, stream, n_launches);
+        return launch_resident_cfg<float, 8, 8, MODEL>(p, stream, n_launches);
+    }
     if (kk <= 128) return launch_resident_cfg<float, 8, 16, MODEL>(p, stream, n_launches);
     if (kk <= 256) return launch_resident_cfg<float, 8, 32, MODEL>(p, stream, n_launches);
 #else
