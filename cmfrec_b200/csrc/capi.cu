@@ -233,6 +233,44 @@ int cmfb200_als_get_collective(cmfb200_als *s, real_t *C, real_t *D, real_t *Ai,
     return s->st.coll->download(C, D, Ai, Bi);
 }
 
+// gram[kk x kk] = G^T G for a dense host matrix G [rows x kk] (reference: the cblas_tsyrk call, src/common.c:3328).
+// The device copy uses the factor layout (rows padded to whole 128-byte lines); `repeats` launches are timed with CUDA
+// events and their mean is returned in *ms_per_launch (optional).
+int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats, float *ms_per_launch)
+{
+    using namespace cmfb200;
+    if (!G || !gram || rows < 1 || kk < 1) return 2;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return 1;
+    const int ld = cmf_ld_for(kk);
+    DevBuf<real_t> dG, dgram, ws;
+    if (!dG.alloc((size_t)rows * ld) || !dgram.alloc((size_t)kk * kk) || !ws.alloc(gram_workspace_elems(kk))) return 1;
+    cudaStream_t st = nullptr;
+    cudaMemsetAsync(dG.p, 0, dG.n * sizeof(real_t), st);
+    if (cudaMemcpy2DAsync(dG.p, (size_t)ld * sizeof(real_t), G, (size_t)kk * sizeof(real_t), (size_t)kk * sizeof(real_t), rows,
+                          cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return 1;
+    int rc = launch_gram(dG.p, ld, rows, kk, dgram.p, ws.p, st);
+    if (rc) return rc;
+    if (repeats > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < repeats && rc == 0; i++) rc = launch_gram(dG.p, ld, rows, kk, dgram.p, ws.p, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms_per_launch) *ms_per_launch = ms / repeats;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (rc) return rc;
+    }
+    if (cudaMemcpyAsync(gram, dgram.p, (size_t)kk * kk * sizeof(real_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
+
 int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }
 
 long long cmfb200_als_launch_count(const cmfb200_als *s) { return s->st.launches; }

@@ -6,14 +6,19 @@
 // registers (4x4 per thread) from shared-memory staged 16-row panels, writes it to a per-slice partial,
 // and a second kernel sums the partials in a fixed order, so the result is run-to-run deterministic.
 #include "sweep.h"
+#include <cstdlib>
 
 namespace cmfb200 {
+
+// gram_tc.cu: per-slice partials on the tensor cores (fp32 library, row widths of 64 / 128 / 256 floats)
+int launch_gram_partials_tc(const real_t *G, int ldG, int_t rows, int kk, int max_slices, real_t *partial, int *nslices_out,
+                            cudaStream_t stream);
 
 namespace {
 
 constexpr int TILE = 64;
 constexpr int PANEL = 16;
-constexpr int MAX_SLICES = 96;
+constexpr int MAX_SLICES = 148;   // one slice per SM in the tensor-core path (gram_tc.cu)
 
 template <typename T>
 __global__ void __launch_bounds__(256) gram_partial_kernel(const T *__restrict__ G, int ldG, int_t rows, int kk,
@@ -114,12 +119,23 @@ size_t gram_workspace_elems(int kk) { return (size_t)MAX_SLICES * kk * kk; }
 int launch_gram(const real_t *G, int ldG, int_t rows, int kk, real_t *gram, real_t *workspace, cudaStream_t stream)
 {
     if (kk < 1) return 2;
+    const int total = kk * kk;
+    {
+        // tensor-core partials where the shape is covered, same fixed-order reduction
+        static const bool use_tc = [] { const char *e = std::getenv("CMFB200_GRAM_TC"); return !e || std::atoi(e) != 0; }();
+        int ns_tc = 0;
+        const int rc = use_tc ? launch_gram_partials_tc(G, ldG, rows, kk, MAX_SLICES, workspace, &ns_tc, stream) : 3;
+        if (rc == 0) {
+            gram_reduce_kernel<real_t><<<(total + 255) / 256, 256, 0, stream>>>(workspace, kk, ns_tc, gram);
+            return cudaGetLastError() == cudaSuccess ? 0 : 1;
+        }
+        if (rc != 3) return rc;
+    }
     const int ntile = (kk + TILE - 1) / TILE;
     const int npairs = ntile * (ntile + 1) / 2;
     const int ns = slices_for(rows, kk);
     dim3 grid(npairs, ns);
     gram_partial_kernel<real_t><<<grid, 256, 0, stream>>>(G, ldG, rows, kk, ntile, ns, workspace);
-    const int total = kk * kk;
     gram_reduce_kernel<real_t><<<(total + 255) / 256, 256, 0, stream>>>(workspace, kk, ns, gram);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

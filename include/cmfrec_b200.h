@@ -171,6 +171,12 @@ void cmfb200_init_biases_twosided(int_t m, int_t n,
  * Holds both orientations of X, both factor matrices and workspaces in HBM.  One state per GPU/process; with
  * world > 1 every rank passes the same matrices, keeps only its own block of rows of each orientation, and the
  * freshly solved blocks are all-gathered over NCCL after every half-sweep.                                   */
+/* gram[kk x kk] = G^T G (full symmetric, row-major) for a dense host matrix G [rows x kk] -- the cblas_tsyrk of the
+ * implicit half-sweep (reference src/common.c:3328, src/collective.c:6276).  fp32 library: tcgen05 tensor cores with
+ * the 3xTF32 split when the padded row width is 64, 128 or 256 floats.  `repeats` > 0 additionally times that many
+ * launches with CUDA events (*ms_per_launch, optional). */
+int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats, float *ms_per_launch);
+
 typedef struct cmfb200_als cmfb200_als;
 
 typedef struct cmfb200_als_options {
