@@ -257,8 +257,10 @@ def main():
     opt.scale_lam = int((not w["implicit"]) and h["scale_lam"])
     opt.max_cg_steps = h["max_cg_steps"]
     opt.rank, opt.world = rank, world
-    idbuf = None
-    if world > 1:
+    idbufs = []
+
+    def fresh_nccl_id():
+        """a new communicator id (single use) made on rank 0 and broadcast through torch.distributed"""
         idt = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             raw = (C.c_ubyte * 128)()
@@ -266,8 +268,11 @@ def main():
             idt = torch.tensor(list(raw), dtype=torch.uint8)
         idt = idt.cuda()
         dist.broadcast(idt, 0)
-        idbuf = (C.c_ubyte * 128)(*idt.cpu().tolist())
-        opt.nccl_id = C.cast(idbuf, C.c_void_p)
+        idbufs.append((C.c_ubyte * 128)(*idt.cpu().tolist()))
+        opt.nccl_id = C.cast(idbufs[-1], C.c_void_p)
+
+    if world > 1:
+        fresh_nccl_id()
     opt.stream = stream
     hnd = C.c_void_p()
     rc = L.cmfb200_als_create(C.byref(hnd), C.byref(opt), *[ptr(t) for t in csr])
@@ -373,8 +378,43 @@ def main():
                        seconds=t_e2e, iterations=K,
                        what="one fit_collective_%s_als call, numpy in / numpy out" % ("implicit" if w["implicit"] else "explicit"))
         else:
-            e2e = dict(value=None, unit="rows/s", h2d_bytes_per_step=None, d2h_bytes_per_step=None,
-                       what="host-pointer entry point is single-GPU in this round")
+            # N > 1: the reference-named entry points take no communicator, so the public call here is the building-block
+            # API one level below them (include/cmfrec_b200.h PART 2) on host buffers: create (partition + upload of this
+            # rank's CSR / CSC blocks), upload of the initial factors, K iterations with their all-gathers, download.
+            assert not (w.get("side") or w.get("implicit_features"))
+            outA = np.zeros((m, w["k"]), dt); outB = np.zeros((n, w["k"]), dt)
+            obA = np.zeros(m, dt) if bA is not None else None
+            obB = np.zeros(n, dt) if bB is not None else None
+
+            def run_blocks(nit):
+                h2 = C.c_void_p()
+                fresh_nccl_id()
+                assert L.cmfb200_als_create(C.byref(h2), C.byref(opt), *[ptr(t) for t in csr]) == 0
+                assert L.cmfb200_als_set_factors(h2, ptr(A0), ptr(bA), ptr(B0), ptr(bB)) == 0
+                assert L.cmfb200_als_iterate(h2, 0, nit, 1 << 30, use_cg, 0) == 0
+                assert L.cmfb200_als_get_factors(h2, ptr(outA), ptr(obA), ptr(outB), ptr(obB)) == 0
+                nzA, nzB, rA, rB = C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_int(0)
+                L.cmfb200_als_local_counts(h2, C.byref(nzA), C.byref(nzB), C.byref(rA), C.byref(rB))
+                L.cmfb200_als_destroy(h2)
+                return nzA.value + nzB.value
+
+            run_blocks(1)
+            barrier()
+            t0 = time.perf_counter()
+            nnz_local = run_blocks(K)
+            barrier()
+            t_e2e = time.perf_counter() - t0
+            tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt.item())
+            wd = dt.itemsize
+            ld = ((w["k"] * wd + 127) // 128) * 128
+            h2d = nnz_local * (4 + wd) + (m + n + 2) * 8 + (m + n) * (ld + wd)
+            d2h = (m + n) * (ld + wd)
+            e2e = dict(value=(m + n) * K / t_e2e, unit="rows/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K,
+                       seconds=t_e2e, iterations=K,
+                       what="cmfb200_als_create + set_factors + iterate + get_factors on host buffers, every rank, max over ranks "
+                            "(h2d / d2h bytes are rank 0's)")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -16,6 +16,34 @@ static int env_or(const char *name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
+bool devbuf_pool_enabled()
+{
+    static const bool on = [] {
+        if (env_or("CMFB200_POOL", 1) == 0) return false;
+        int dev = 0, supported = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+        if (!supported) return false;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) { cudaGetLastError(); return false; }
+        unsigned long long keep = ~0ull;   // never hand freed memory back on its own
+        if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) { cudaGetLastError(); return false; }
+        return true;
+    }();
+    return on;
+}
+
+void devbuf_trim_pool()
+{
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+}
+
 static int long_row_threshold()
 {
     static int v = -1;

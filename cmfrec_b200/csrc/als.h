@@ -12,19 +12,49 @@
 
 namespace cmfb200 {
 
+// Device allocations come from the device's default stream-ordered memory pool with its release threshold raised, so
+// that the ~20 buffers of a fit call (hundreds of MB at ML10M shape) are recycled by the next call instead of going
+// through cudaMalloc / cudaFree every time (measured: 100-500 ms per call, profiles/README.md).  CMFB200_POOL=0 falls
+// back to cudaMalloc / cudaFree; cmfb200_trim_pool() hands the cached memory back to the driver.
+bool devbuf_pool_enabled();
+void devbuf_trim_pool();
+
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool pooled = false;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release()
+    {
+        if (p) {
+            if (pooled) {
+                // like cudaFree, wait for whatever may still be using the buffer (any stream), then return it to the pool
+                cudaDeviceSynchronize();
+                cudaFreeAsync(p, nullptr);
+            } else {
+                cudaFree(p);
+            }
+        }
+        p = nullptr;
+        n = 0;
+    }
     bool alloc(size_t count)
     {
         release();
         n = count;
         if (count == 0) return true;
+        pooled = devbuf_pool_enabled();
+        if (pooled) {
+            if (cudaMallocAsync((void **)&p, count * sizeof(T), nullptr) == cudaSuccess) {
+                // usable from every stream once the allocation itself has completed
+                return cudaStreamSynchronize(nullptr) == cudaSuccess;
+            }
+            cudaGetLastError();
+            pooled = false;
+        }
         return cudaMalloc((void **)&p, count * sizeof(T)) == cudaSuccess;
     }
 };

@@ -271,6 +271,8 @@ int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats,
     return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
 }
 
+void cmfb200_trim_pool(void) { cmfb200::devbuf_trim_pool(); }
+
 int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }
 
 long long cmfb200_als_launch_count(const cmfb200_als *s) { return s->st.launches; }

@@ -7,8 +7,8 @@
 //                        The integer outputs are identical to the reference's, entry for entry.
 //   centring             x - glob_mean in real_t                         src/common.c:3632-3644
 //   bias initialisation  initialize_biases_twosided / _onesided          src/common.c:4643-4669, 4799-4825, 4266-4289
-//                        one thread walks one row sequentially with the reference's operations in the reference's
-//                        order (running mean in double, residual formed in real_t), so results are bit-identical.
+//                        one warp per row: coalesced fetch of 32 entries, then the reference's sequential chain
+//                        (running mean in double, residual formed in real_t) in its order, so results are bit-identical.
 #include "device_prep.h"
 #include <cub/cub.cuh>
 #include <cstdio>
@@ -47,30 +47,74 @@ template <typename T> __global__ void subtract_kernel(T *x, size_t n, T mu)
     if (i < n) x[i] = x[i] - mu;
 }
 
-// one sweep of the bias initialisation over one orientation: bias[r] = shrunken running mean of (x - other[idx])
+// one sweep of the bias initialisation over one orientation: bias[r] = shrunken running mean of (x - other[idx]).
+// One WARP per row: the lanes fetch 32 consecutive entries (coalesced values and indices, gathered biases), form the
+// residuals in real_t and the reciprocals of the running counts, and park them in shared memory; then every lane walks
+// the same sequential chain  mean += (resid - mean) / count  over the 32 parked entries in the reference's order, so
+// the result is bit-identical to the reference's scalar loop.  The division is the correctly rounded quotient from a
+// correctly rounded reciprocal (q0 = d * y, rem = fma(-q0, n, d) exact, q = fma(rem, y, q0): Markstein's final step,
+// exact for integer n), which keeps the IEEE division routine off the chain.
+constexpr int kBiasWarps = 8;
+
 template <typename T>
-__global__ void bias_sweep_kernel(int_t rows, const size_t *__restrict__ ptr, const int_t *__restrict__ idx,
-                                  const T *__restrict__ val, const T *__restrict__ other, T lam, bool scale_lam,
-                                  bool clamp_count_to_one, bool shrink_empty, T *__restrict__ out)
+__global__ void __launch_bounds__(kBiasWarps * 32)
+bias_sweep_kernel(int_t rows, const size_t *__restrict__ ptr, const int_t *__restrict__ idx, const T *__restrict__ val,
+                  const T *__restrict__ other, T lam, bool scale_lam, bool clamp_count_to_one, bool shrink_empty,
+                  T *__restrict__ out)
 {
-    const int_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_resid[kBiasWarps][32], s_rcp[kBiasWarps][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int_t r = blockIdx.x * kBiasWarps + w;
     if (r >= rows) return;
     const size_t b = ptr[r], e = ptr[r + 1];
     double mean = 0.;
-    // the running mean is a sequential chain, but the (gathered) residuals are not: fetch 8 at a time
-    size_t t = b;
-    for (; t + 8 <= e; t += 8) {
-        T resid[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) resid[u] = other ? (T)(val[t + u] - other[idx[t + u]]) : val[t + u];
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-            mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid[u], mean), (double)(t + u - b + 1)));
+    // this lane's entry of the 32-entry chunk starting at t0: residual (as the reference forms it, in real_t) and the
+    // reciprocal of its running count
+    auto fetch = [&](size_t t0, double &resid, double &rcp) {
+        const size_t t = t0 + lane;
+        resid = 0.;
+        rcp = 0.;
+        if (t < e) {
+            resid = (double)(other ? (T)(val[t] - other[idx[t]]) : val[t]);
+            rcp = __drcp_rn((double)(t - b + 1));
+        }
+    };
+    // the fetches run two chunks ahead of the chain: on the longest row the chain, not the memory latency, sets the pace
+    bool suspicious = false;
+    double res1, rcp1, res2, rcp2;
+    fetch(b, res1, rcp1);
+    fetch(b + 32, res2, rcp2);
+    for (size_t t0 = b; t0 < e; t0 += 32) {
+        s_resid[w][lane] = res1;
+        s_rcp[w][lane] = rcp1;
+        res1 = res2;
+        rcp1 = rcp2;
+        fetch(t0 + 64, res2, rcp2);
+        __syncwarp();
+        const int n = e - t0 < 32 ? (int)(e - t0) : 32;
+        double cnt = (double)(t0 - b);
+#pragma unroll 4
+        for (int u = 0; u < n; u++) {
+            cnt += 1.;
+            const double d = __dsub_rn(s_resid[w][u], mean), y = s_rcp[w][u];
+            const double q0 = __dmul_rn(d, y);
+            const double rem = __fma_rn(-q0, cnt, d);
+            mean = __dadd_rn(mean, __fma_rn(rem, y, q0));
+            // operands for which the three-step quotient is not guaranteed exact (never seen on ratings; checked off the
+            // chain: nothing below depends on it until the row is finished)
+            const double ad = fabs(d);
+            suspicious |= (ad != 0. && ad < 1e-280) || !(ad < 1e280);
+        }
+        __syncwarp();
     }
-    for (; t < e; t++) {
-        const T resid = other ? (T)(val[t] - other[idx[t]]) : val[t];
-        mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid, mean), (double)(t - b + 1)));
+    if (suspicious) {   // warp-uniform: every lane walked the same chain; redo the row with the IEEE division routine
+        mean = 0.;
+        for (size_t t = b; t < e; t++) {
+            const T resid = other ? (T)(val[t] - other[idx[t]]) : val[t];
+            mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid, mean), (double)(t - b + 1)));
+        }
     }
+    if (lane != 0) return;
     const size_t cnt = e - b;
     if (cnt > 0 || shrink_empty) {
         const double c = (double)cnt;
@@ -131,11 +175,11 @@ int device_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const int
     if (fabs((double)lam_item) < (double)CMF_EPS) lam_item = CMF_EPS;
     cudaMemsetAsync(d_biasA, 0, (size_t)m * sizeof(real_t), stream);
     cudaMemsetAsync(d_biasB, 0, (size_t)n * sizeof(real_t), stream);
-    const int threads = 64;
+
     for (int s = 0; s < 5; s++) {
-        bias_sweep_kernel<real_t><<<(n + threads - 1) / threads, threads, 0, stream>>>(n, csc_p, csc_i, csc_v, d_biasA, lam_item,
+        bias_sweep_kernel<real_t><<<(n + kBiasWarps - 1) / kBiasWarps, kBiasWarps * 32, 0, stream>>>(n, csc_p, csc_i, csc_v, d_biasA, lam_item,
                                                                                         scale_lam, true, true, d_biasB);
-        bias_sweep_kernel<real_t><<<(m + threads - 1) / threads, threads, 0, stream>>>(m, csr_p, csr_i, csr_v, d_biasB, lam_user,
+        bias_sweep_kernel<real_t><<<(m + kBiasWarps - 1) / kBiasWarps, kBiasWarps * 32, 0, stream>>>(m, csr_p, csr_i, csr_v, d_biasB, lam_user,
                                                                                         scale_lam, false, false, d_biasA);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -145,8 +189,8 @@ int device_init_biases_onesided(int_t rows, const size_t *ptr, const real_t *val
                                 cudaStream_t stream)
 {
     if (fabs((double)lam) < (double)CMF_EPS) lam = CMF_EPS;
-    const int threads = 64;
-    bias_sweep_kernel<real_t><<<(rows + threads - 1) / threads, threads, 0, stream>>>(rows, ptr, nullptr, val, nullptr, lam,
+
+    bias_sweep_kernel<real_t><<<(rows + kBiasWarps - 1) / kBiasWarps, kBiasWarps * 32, 0, stream>>>(rows, ptr, nullptr, val, nullptr, lam,
                                                                                        scale_lam, true, true, d_bias);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -628,10 +628,10 @@ template <int MODEL> int dispatch_resident(const CgSweepParams &p, cudaStream_t 
     if (kk <= 32) return launch_resident_cfg<float, 8, 4, MODEL>(p, stream, n_launches);
     if (kk <= 64) {
         // 8 lanes per entry read whole 128-byte lines (half the L1 wavefronts of the 4-lane layout on streamed gathers)
-        // (measured: 1.84 vs 1.87 ms / iteration at ML10M shape, 5.67 vs 7.13 ms at LastFM shape, profiles/README.md)
+        // (measured: 1.84 vs 1.87 ms / iteration at ML10M shape, 5.67 vs 7.13 ms at LastFM shape; a third thread block
+        // per SM at 80 registers spills and loses: 2.15 / 7.7 ms -- profiles/README.md)
         const int v = env_int("CMFB200_RES_CFG64", 1);
         if (v == 0) return launch_resident_cfg<float, 16, 4, MODEL>(p, stream, n_launches);
-        if (v == 3) return launch_resident_cfg<float, 8, 8, MODEL, 3>(p, stream, n_launches);
         return launch_resident_cfg<float, 8, 8, MODEL>(p, stream, n_launches);
     }
     if (kk <= 128) return launch_resident_cfg<float, 8, 16, MODEL>(p, stream, n_launches);

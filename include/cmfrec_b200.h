@@ -177,6 +177,10 @@ void cmfb200_init_biases_twosided(int_t m, int_t n,
  * launches with CUDA events (*ms_per_launch, optional). */
 int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats, float *ms_per_launch);
 
+/* Device buffers are recycled between calls through the device's default memory pool (CMFB200_POOL=0 disables it);
+ * this hands the cached memory back to the driver. */
+void cmfb200_trim_pool(void);
+
 typedef struct cmfb200_als cmfb200_als;
 
 typedef struct cmfb200_als_options {
