@@ -26,6 +26,10 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -81,6 +85,25 @@ def algorithmic_bytes(w, m, n, nnz, dt):
     half = lambda rows, opp: (nnz * (k1 * wd + 4 + wd + extra_gather) + rows * (8 + 2 * k1 * wd)
                               + (opp * w["k"] * wd if w["implicit"] else 0) + rows * w.get("side", 0) * wd)
     return half(n, m), half(m, n)       # (B sweep, A sweep)
+
+
+def measured_dram_traffic(w):
+    """DRAM bytes per launch of the row-solve kernel from the committed `ncu --set full` capture of this workload's
+    shape (profiles/, condensed by tools/summarize_ncu.py); None when no capture of that shape / model is committed."""
+    import csv
+    if not w["use_cg"] or w["k"] != 64 or w.get("side") or w.get("implicit_features"):
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_cg_sweep_%s.csv" % w["shape"])
+    if not os.path.exists(path):
+        return None, None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}
+    rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    per = [float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]] for r in rows[2:] if "cg_resident_kernel" in r[1]]
+    if not per:
+        return None, None
+    return sum(per) / len(per), os.path.relpath(path, ROOT)
 
 
 class ClockSampler:
@@ -341,8 +364,10 @@ def main():
     bytes_per_launch = (bytes_B + bytes_A) / 2.0 / world
     avg_ms = kernel_ms / max(kernel_launches, 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                    kernel="cg_sweep_kernel" if w["use_cg"] else "chol_sweep_kernel", avg_launch_ms=avg_ms,
+    traffic, traffic_src = measured_dram_traffic(w)
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    traffic_unit="GB per launch (dram__bytes_read.sum + dram__bytes_write.sum)", traffic_source=traffic_src,
+                    kernel="cg_resident_kernel" if w["use_cg"] else "chol_sweep_kernel", avg_launch_ms=avg_ms,
                     launches_timed=int(kernel_launches), algorithmic_bytes_per_launch=bytes_per_launch,
                     kernel_share_of_step=kernel_ms / total_ms if total_ms else None, peak_source=peak_src,
                     B_sweep_ms=kt[0].value / max(kc[0].value, 1), A_sweep_ms=kt[1].value / max(kc[1].value, 1))
@@ -387,8 +412,7 @@ def main():
             obB = np.zeros(n, dt) if bB is not None else None
 
             def run_blocks(nit):
-                h2 = C.c_void_p()
-                fresh_nccl_id()
+                h2 = C.c_void_p()      # same communicator id as above: the library reuses the communicator
                 assert L.cmfb200_als_create(C.byref(h2), C.byref(opt), *[ptr(t) for t in csr]) == 0
                 assert L.cmfb200_als_set_factors(h2, ptr(A0), ptr(bA), ptr(B0), ptr(bB)) == 0
                 assert L.cmfb200_als_iterate(h2, 0, nit, 1 << 30, use_cg, 0) == 0

@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace cmfb200 {
 
@@ -57,10 +58,19 @@ int check(int rc, const char *what)
 }
 }  // namespace
 
-NcclLink::~NcclLink()
+// Communicators are cached per process under the unique id they were created from: a second state created with the
+// same id reuses the communicator instead of paying ncclCommInitRank again (seconds), which is what a caller that fits
+// many models in one process wants.  They live until the process exits.
+namespace {
+struct CachedComm { id_t id; int rank, world; void *comm; };
+std::vector<CachedComm> &comm_cache()
 {
-    if (comm && api().ok) api().CommDestroy(comm);
+    static std::vector<CachedComm> c;
+    return c;
 }
+}  // namespace
+
+NcclLink::~NcclLink() {}
 
 int NcclLink::unique_id(void *out128)
 {
@@ -80,7 +90,14 @@ int NcclLink::init(const void *id128, int rank_, int world_)
     world = world_;
     id_t id;
     std::memcpy(&id, id128, sizeof(id));
-    return check(a.CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+    for (const CachedComm &c : comm_cache())
+        if (c.rank == rank && c.world == world && std::memcmp(&c.id, &id, sizeof(id)) == 0) {
+            comm = c.comm;
+            return 0;
+        }
+    if (check(a.CommInitRank(&comm, world, id, rank), "ncclCommInitRank")) return 1;
+    comm_cache().push_back(CachedComm{id, rank, world, comm});
+    return 0;
 }
 
 int NcclLink::all_gather_inplace(void *base, size_t bytes_per_rank, cudaStream_t stream)

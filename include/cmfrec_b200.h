@@ -192,7 +192,8 @@ typedef struct cmfb200_als_options {
     int scale_lam;
     int max_cg_steps;
     int rank, world;           /* world > 1 needs nccl_id */
-    const void *nccl_id;       /* 128 bytes from cmfb200_nccl_unique_id, identical on all ranks */
+    const void *nccl_id;       /* 128 bytes from cmfb200_nccl_unique_id, identical on all ranks; states created with an id
+                                * seen before in this process reuse its communicator */
     void *stream;              /* cudaStream_t to enqueue on (NULL = default stream) */
 } cmfb200_als_options;
 
