@@ -2,6 +2,8 @@
 // (reference optimizeA Case 1 src/common.c:2793-2900, Case 3 :3117-3203; optimizeA_collective general case
 // src/collective.c:5566-5968).  None of these dominate an iteration; they are written for clarity and determinism.
 #include "dense_small.h"
+#include "device_utils.cuh"
+#include <cstdint>
 #include <cmath>
 #include <vector>
 
@@ -258,11 +260,130 @@ int launch_rows_times_small(const real_t *M, int ldm, int p, const real_t *S, in
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+namespace {
+
+// Same product with 16-byte gathers: 8 lanes read one whole 128-byte line of an opposing row per load instruction,
+// 4 entries per step, the (column) indices of 32 entries fetched coalesced and handed round with shuffles; every lane
+// keeps NV vector accumulators, the four groups of a warp are combined with shuffles at the end of the row.
+// Needs 16-byte aligned rows of F (ldf a multiple of the vector width) and kk <= 8 * NV * (16 / sizeof(T)).
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) spmm_ones_vec_kernel(const size_t *__restrict__ ptr, const int_t *__restrict__ idx,
+                                                            const int_t *__restrict__ order, int_t n_rows, int_t n_long,
+                                                            const T *__restrict__ F, int ldf, int kk, T alpha, bool accumulate,
+                                                            T *__restrict__ Y, int ldy)
+{
+    constexpr int VN = 16 / (int)sizeof(T);
+    typedef typename VecOf<T>::type Vec;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *red = reinterpret_cast<T *>(smem_raw);   // [8][8 * NV * VN]
+    constexpr int KP = 8 * NV * VN;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
+    const int pieces = (kk + VN - 1) / VN;
+    const int n_slots = n_long + (n_rows - n_long + 7) / 8;
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        const bool team = slot < n_long;
+        const int i = team ? slot : n_long + (slot - n_long) * 8 + w;
+        if (i >= n_rows) continue;   // warp-uniform; team slots never take this branch
+        const int_t row = order[i];
+        const size_t b = ptr[row], e = ptr[row + 1];
+        T acc[NV][VN];
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int q = 0; q < VN; q++) acc[v][q] = T(0);
+        // 32-entry chunks: this warp's chunks are w, w + 8, ... of a team row, all of a warp row
+        for (size_t t0 = b + (team ? (size_t)w * 32 : 0); t0 < e; t0 += team ? 256 : 32) {
+            const size_t t = t0 + lane;
+            const int col_r = t < e ? idx[t] : -1;
+            const int left = e - t0 < 32 ? (int)(e - t0) : 32;
+#pragma unroll 4
+            for (int st = 0; st < 8; st++) {
+                if (st * 4 >= left) break;   // warp-uniform
+                const int col = __shfl_sync(CMF_FULL_MASK, col_r, st * 4 + g);
+                if (col >= 0) {
+                    const Vec *frow = reinterpret_cast<const Vec *>(F + (size_t)col * (size_t)ldf);
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        if (v * 8 + l < pieces) {
+                            const Vec x = __ldg(frow + v * 8 + l);
+                            const T *px = reinterpret_cast<const T *>(&x);
+#pragma unroll
+                            for (int q = 0; q < VN; q++) acc[v][q] += px[q];
+                        }
+                    }
+                }
+            }
+        }
+        // combine the four groups of the warp
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int q = 0; q < VN; q++) {
+                acc[v][q] += __shfl_xor_sync(CMF_FULL_MASK, acc[v][q], 8);
+                acc[v][q] += __shfl_xor_sync(CMF_FULL_MASK, acc[v][q], 16);
+            }
+        if (team) {
+            __syncthreads();
+            if (g == 0) {
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+#pragma unroll
+                    for (int q = 0; q < VN; q++) red[w * KP + (v * 8 + l) * VN + q] = acc[v][q];
+            }
+            __syncthreads();
+            if (w == 0 && g == 0) {
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+#pragma unroll
+                    for (int q = 0; q < VN; q++) {
+                        T s = T(0);
+                        for (int ww = 0; ww < 8; ww++) s += red[ww * KP + (v * 8 + l) * VN + q];
+                        acc[v][q] = s;
+                    }
+            }
+        }
+        if ((!team || w == 0) && g == 0) {
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+#pragma unroll
+                for (int q = 0; q < VN; q++) {
+                    const int c = (v * 8 + l) * VN + q;
+                    if (c < kk) {
+                        T *o = Y + (size_t)row * ldy + c;
+                        *o = accumulate ? fma(alpha, acc[v][q], *o) : alpha * acc[v][q];
+                    }
+                }
+        }
+        if (team) __syncthreads();
+    }
+}
+
+}  // namespace
+
 int launch_spmm_ones(const CsrView &X, const SweepPlan &plan, const real_t *F, int ldf, int kk, real_t alpha, bool accumulate,
                      real_t *Y, int ldy, cudaStream_t stream)
 {
     if (plan.n_rows < 1) return 0;
     const int n_slots = plan.n_long + (plan.n_rows - plan.n_long + 7) / 8;
+    {
+        constexpr int VN = 16 / (int)sizeof(real_t);
+        const int pieces = (kk + VN - 1) / VN;
+        const bool aligned = ldf % VN == 0 && ((uintptr_t)F & 15u) == 0 && pieces * VN <= ldf;
+        if (aligned && pieces <= 32) {
+            const int blocks_v = std::min(n_slots, 8 * sm_count());
+            if (pieces <= 8) {
+                spmm_ones_vec_kernel<real_t, 1><<<blocks_v, 256, (size_t)8 * 8 * 1 * VN * sizeof(real_t), stream>>>(
+                    X.ptr, X.idx, plan.order, plan.n_rows, plan.n_long, F, ldf, kk, alpha, accumulate, Y, ldy);
+            } else if (pieces <= 16) {
+                spmm_ones_vec_kernel<real_t, 2><<<blocks_v, 256, (size_t)8 * 8 * 2 * VN * sizeof(real_t), stream>>>(
+                    X.ptr, X.idx, plan.order, plan.n_rows, plan.n_long, F, ldf, kk, alpha, accumulate, Y, ldy);
+            } else {
+                spmm_ones_vec_kernel<real_t, 4><<<blocks_v, 256, (size_t)8 * 8 * 4 * VN * sizeof(real_t), stream>>>(
+                    X.ptr, X.idx, plan.order, plan.n_rows, plan.n_long, F, ldf, kk, alpha, accumulate, Y, ldy);
+            }
+            return cudaGetLastError() == cudaSuccess ? 0 : 1;
+        }
+    }
     int blocks = std::min(n_slots, 8 * sm_count());
     spmm_ones_kernel<real_t><<<blocks, 256, (size_t)8 * kk * sizeof(real_t), stream>>>(X.ptr, X.idx, plan.order, plan.n_rows,
                                                                                         plan.n_long, F, ldf, kk, alpha,

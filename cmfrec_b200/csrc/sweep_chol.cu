@@ -18,7 +18,19 @@ namespace cmfb200 {
 
 namespace {
 
-constexpr int NB = 16;       // stored entries staged per round
+// four consecutive elements from 16-byte aligned shared memory with vector loads
+__device__ __forceinline__ void load4(const float *p, float (&v)[4])
+{
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double *p, double (&v)[4])
+{
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+constexpr int NB = 32;       // stored entries staged per round
 
 // NT threads per block, TPT register tiles per thread; MG: the kd x kd matrix does not fit in shared memory
 // and lives in a per-block slice of a global workspace instead (it stays in L2).
@@ -47,6 +59,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
         tile_map[2 * t] = (unsigned short)ti;
         tile_map[2 * t + 1] = (unsigned short)(ti + rem);
     }
+    for (int i = tid; i < NB * kdp; i += NT) gs[i] = T(0);   // columns beyond the copied pieces stay zero
     __syncthreads();
     int my_ti[TPT], my_tj[TPT];
 #pragma unroll
@@ -101,13 +114,24 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
                     xr[tid] = x - ob;
                 }
             }
-            for (int i = tid; i < nb * kdp; i += NT) {
-                const int b = i / kdp, c = i - b * kdp;
-                const int col = p.X.idx[beg + e0 + b];
-                T v = T(0);
-                if (c < kk) v = __ldg(p.G + (size_t)col * p.ldG + c);
-                else if (c == kk && hb) v = T(1);
-                gs[i] = v;
+            // 16 threads per staged row, 16-byte pieces (the padding columns of G are zero and its rows are whole
+            // 128-byte lines, so whole pieces can be copied; the bias column, which may share the last piece, is patched
+            // in the register before the store)
+            {
+                constexpr int VN = 16 / (int)sizeof(T);
+                typedef typename VecOf<T>::type Vec;
+                const int ppr = (kk + VN - 1) / VN;
+                for (int b = tid >> 4; b < nb; b += NT / 16) {
+                    const int col = p.X.idx[beg + e0 + b];
+                    const T *grow = p.G + (size_t)col * (size_t)p.ldG;
+                    for (int pc = tid & 15; pc < ppr; pc += 16) {
+                        Vec v = __ldg(reinterpret_cast<const Vec *>(grow) + pc);
+                        if (hb && pc * VN <= kk && kk < (pc + 1) * VN) reinterpret_cast<T *>(&v)[kk - pc * VN] = T(1);
+                        *reinterpret_cast<Vec *>(gs + (size_t)b * kdp + pc * VN) = v;
+                    }
+                }
+                // the bias column when it starts a piece of its own (never written by the copy above)
+                if (hb && kk % VN == 0 && tid < nb) gs[(size_t)tid * kdp + kk] = T(1);
             }
             __syncthreads();
             // ---- rank-nb update of the register tiles and of the right-hand side
@@ -118,10 +142,8 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
                 for (int s = 0; s < TPT; s++) {
                     if (my_ti[s] >= 0) {
                         T gi[4], gj[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) gi[i] = g[4 * my_ti[s] + i];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) gj[j] = g[4 * my_tj[s] + j];
+                        load4(g + 4 * my_ti[s], gi);
+                        load4(g + 4 * my_tj[s], gj);
                         if (IMPLICIT) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) gi[i] *= wb;
@@ -268,6 +290,7 @@ template <int MODEL> int dispatch_chol(const CgSweepParams &p, cudaStream_t stre
     const int tpt256 = (ntiles + 255) / 256;
     const int tpt512 = (ntiles + 511) / 512;
     if (in_smem) {
+        if (ntiles <= 160) return launch_tpt<T, 160, 1, MODEL, false>(p, kd, kdp, ntile_rows, stream);   // k = 64 (+ bias): 153 tiles
         if (tpt256 <= 1) return launch_tpt<T, 256, 1, MODEL, false>(p, kd, kdp, ntile_rows, stream);
         if (tpt256 <= 2) return launch_tpt<T, 256, 2, MODEL, false>(p, kd, kdp, ntile_rows, stream);
         if (tpt256 <= 3) return launch_tpt<T, 256, 3, MODEL, false>(p, kd, kdp, ntile_rows, stream);

@@ -1,0 +1,13 @@
+#!/bin/bash
+S=$(date +%s)
+timeout 900 python -m pytest tests/test_gpu_sweeps.py tests/test_gpu_fit.py -m gpu -q -x -k "chol or fit" 2>&1 | tail -3
+qb() { echo "== $*"; env "$@" timeout 300 python tools/quick_bench.py --shape $SHAPE --k $K --implicit $IMP --solver chol --iters 3 $EXTRA 2>&1 | grep -E "RESULT|Error|error|assert" ; }
+SHAPE=ml10m K=64 IMP=0 EXTRA=""; qb A=1
+SHAPE=lastfm K=64 IMP=1; qb A=1
+SHAPE=ml10m K=128 IMP=0 EXTRA="--dtype f64"; qb A=1
+mkdir -p gpurun_out/prof2
+for w in ml10m_explicit_cg_k64_f32_implicit_features ml10m_explicit_chol_k128_f64_sideinfo; do
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/prof2/launches_$w.csv \
+     python bench.py --workload $w --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+done
+echo "total $(( $(date +%s) - S )) s"
