@@ -379,15 +379,22 @@ def main():
     if not args.no_e2e:
         K = args.steps
         if world == 1:
+            # the caller's buffers: COO triplets and the output factors in pinned host memory, handed to the entry point as
+            # they are (the library never writes to its inputs, so no defensive copies)
+            pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()
+            pa, pb, px = pin(a), pin(b), pin(x)
+            outbuf = dict(A=pin(np.zeros((m, w["k"]), dt)), B=pin(np.zeros((n, w["k"]), dt)))
             if w["implicit"]:
-                run = lambda nit: fit_implicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=nit,
-                                               use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu)
+                run = lambda nit: fit_implicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=nit,
+                                               use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
+                                               copy_inputs=False, out=outbuf)
             else:
+                outbuf.update(biasA=pin(np.zeros(m, dt)), biasB=pin(np.zeros(n, dt)))
                 U, I = side_info(w, m, n, dt)
                 extra = dict(U=U, I=I, add_implicit_features=bool(w.get("implicit_features")), w_implicit=w.get("w_implicit", 1.0))
-                run = lambda nit: fit_explicit(L, dt, a, b, x, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
+                run = lambda nit: fit_explicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
                                                niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
-                                               **extra)
+                                               copy_inputs=False, out=outbuf, **extra)
             run(1)
             run(2)
             torch.cuda.synchronize()
@@ -401,7 +408,7 @@ def main():
             d2h = (m + n) * ld
             e2e = dict(value=(m + n) * K / t_e2e, unit="rows/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K,
                        seconds=t_e2e, iterations=K,
-                       what="one fit_collective_%s_als call, numpy in / numpy out" % ("implicit" if w["implicit"] else "explicit"))
+                       what="one fit_collective_%s_als call, pinned host buffers in / out" % ("implicit" if w["implicit"] else "explicit"))
         else:
             # N > 1: the reference-named entry points take no communicator, so the public call here is the building-block
             # API one level below them (include/cmfrec_b200.h PART 2) on host buffers: create (partition + upload of this

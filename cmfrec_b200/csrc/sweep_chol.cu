@@ -186,20 +186,42 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
         }
         __syncthreads();
 
-        // ---- Cholesky, lower, right-looking
+        // ---- Cholesky, lower, left-looking (Cholesky-Crout): column j of L from the rows of L already known,
+        //      L[i][j] = (M[i][j] - sum_{t<j} L[i][t] L[j][t]) / L[j][j].  Four adjacent lanes share one row's dot product
+        //      (a quarter of the range each, two shuffles), so that one round covers NT / 4 rows; with a row stride of
+        //      4 (mod 32) elements the 8 rows x 4 parts of a warp fall on 32 different banks.  One sixth of the
+        //      instructions of the right-looking update with its short inner loops (profiles/README.md).
         const int warp = tid >> 5, lane = tid & 31;
-        for (int j = 0; j < kd; j++) {
-            const T d = sqrt(M[j * kdp + j]);
-            const T inv = T(1) / d;
-            for (int i = j + 1 + tid; i < kd; i += NT) colbuf[i] = M[i * kdp + j] * inv;
-            if (tid == 0) diag[j] = d;
-            __syncthreads();
-            for (int i = j + 1 + warp; i < kd; i += NT / 32) {
-                const T lij = colbuf[i];
-                for (int c = j + 1 + lane; c <= i; c += 32) M[i * kdp + c] = fma(-lij, colbuf[c], M[i * kdp + c]);
-                if (lane == 0) M[i * kdp + j] = lij;
+        {
+            constexpr int PARTS = 4;
+            const int part = tid & (PARTS - 1);
+            for (int j = 0; j < kd; j++) {
+                const T *Lj = M + (size_t)j * kdp;
+                for (int base = j; base < kd; base += NT / PARTS) {   // block-uniform
+                    const int i = base + tid / PARTS;
+                    const bool active = i < kd;
+                    T s0 = T(0), s1 = T(0);
+                    if (active) {
+                        const T *Li = M + (size_t)i * kdp;
+                        int t = part;
+                        for (; t + PARTS < j; t += 2 * PARTS) {
+                            s0 = fma(Li[t], Lj[t], s0);
+                            s1 = fma(Li[t + PARTS], Lj[t + PARTS], s1);
+                        }
+                        if (t < j) s0 = fma(Li[t], Lj[t], s0);
+                    }
+                    T sum = s0 + s1;
+                    sum += __shfl_xor_sync(CMF_FULL_MASK, sum, 1);
+                    sum += __shfl_xor_sync(CMF_FULL_MASK, sum, 2);
+                    if (active && part == 0) colbuf[i] = M[(size_t)i * kdp + j] - sum;
+                }
+                __syncthreads();
+                const T d = sqrt(colbuf[j]);
+                const T inv = T(1) / d;
+                for (int i = j + 1 + tid; i < kd; i += NT) M[(size_t)i * kdp + j] = colbuf[i] * inv;
+                if (tid == 0) diag[j] = d;
+                __syncthreads();
             }
-            __syncthreads();
         }
 
         // ---- L y = rhs, L^T a = y  (one warp; lane owns entries lane, lane+32, ...)

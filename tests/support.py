@@ -39,14 +39,17 @@ def synth_coo(m, n, nnz, dtype, seed=0, kind="ratings", dedup=True, zipf=True):
 def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, item_bias=True, center=True,
                  scale_lam=False, niter=3, use_cg=True, max_cg_steps=3, finalize_chol=False, seed=1, nthreads=4,
                  w_main=1.0, lam_unique=None, precompute=False, k_main=0, U=None, I=None, add_implicit_features=False,
-                 w_user=1.0, w_item=1.0, w_implicit=1.0, center_side=True):
-    """Call fit_collective_explicit_als (reference src/cmfrec.h:1851) on `lib`; returns dict of outputs."""
+                 w_user=1.0, w_item=1.0, w_implicit=1.0, center_side=True, copy_inputs=True, out=None):
+    """Call fit_collective_explicit_als (reference src/cmfrec.h:1851) on `lib`; returns dict of outputs.
+    copy_inputs=False passes the caller's index / value arrays as they are (the reference may overwrite X; this
+    repo's library never writes to its inputs); `out` may hold preallocated A, B, biasA, biasB (e.g. pinned memory)."""
     dt = np.dtype(dtype)
     kk = k + k_main
-    A = np.zeros((m, kk), dt)
-    B = np.zeros((n, kk), dt)
-    biasA = np.zeros(m, dt)
-    biasB = np.zeros(n, dt)
+    out = out or {}
+    A = out["A"] if "A" in out else np.zeros((m, kk), dt)
+    B = out["B"] if "B" in out else np.zeros((n, kk), dt)
+    biasA = out["biasA"] if "biasA" in out else np.zeros(m, dt)
+    biasB = out["biasB"] if "biasB" in out else np.zeros(n, dt)
     glob_mean = np.zeros(1, dt)
     sA = np.zeros(1, dt)
     sB = np.zeros(1, dt)
@@ -56,9 +59,13 @@ def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, 
     Bpb = np.zeros((n, kk + 1), dt) if (precompute and has_bias) else None
     BtB = np.zeros((kk + ub, kk + ub), dt) if precompute else None
     TBt = np.zeros((n, kk + ub), dt) if precompute else None
-    ixA = np.ascontiguousarray(ixA, np.int32).copy()
-    ixB = np.ascontiguousarray(ixB, np.int32).copy()
-    X = np.ascontiguousarray(X, dt).copy()
+    if copy_inputs:
+        ixA = np.ascontiguousarray(ixA, np.int32).copy()
+        ixB = np.ascontiguousarray(ixB, np.int32).copy()
+        X = np.ascontiguousarray(X, dt).copy()
+    else:
+        assert ixA.dtype == np.int32 and ixB.dtype == np.int32 and X.dtype == dt
+        assert ixA.flags.c_contiguous and ixB.flags.c_contiguous and X.flags.c_contiguous
     p = 0 if U is None else U.shape[1]
     q = 0 if I is None else I.shape[1]
     Uc = None if U is None else np.ascontiguousarray(U, dt).copy()
@@ -83,17 +90,19 @@ def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, 
 
 def fit_implicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=5.0, alpha=1.0, niter=3, use_cg=True, max_cg_steps=3,
                  finalize_chol=False, seed=1, nthreads=4, w_main=1.0, adjust_weight=False, apply_log_transf=False,
-                 precompute=False, k_main=0):
-    """Call fit_collective_implicit_als (reference src/cmfrec.h:1893) on `lib`."""
+                 precompute=False, k_main=0, copy_inputs=True, out=None):
+    """Call fit_collective_implicit_als (reference src/cmfrec.h:1893) on `lib` (copy_inputs / out: see fit_explicit)."""
     dt = np.dtype(dtype)
     kk = k + k_main
-    A = np.zeros((m, kk), dt)
-    B = np.zeros((n, kk), dt)
+    out = out or {}
+    A = out["A"] if "A" in out else np.zeros((m, kk), dt)
+    B = out["B"] if "B" in out else np.zeros((n, kk), dt)
     wmm = np.zeros(1, dt)
     BtB = np.zeros((kk, kk), dt) if precompute else None
-    ixA = np.ascontiguousarray(ixA, np.int32).copy()
-    ixB = np.ascontiguousarray(ixB, np.int32).copy()
-    X = np.ascontiguousarray(X, dt).copy()
+    if copy_inputs:
+        ixA = np.ascontiguousarray(ixA, np.int32).copy()
+        ixB = np.ascontiguousarray(ixB, np.int32).copy()
+        X = np.ascontiguousarray(X, dt).copy()
     rc = lib.fit_collective_implicit_als(
         ptr(A), ptr(B), None, None, True, seed, None, None, m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size,
         lam, None, 0.0, None, None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False,

@@ -205,3 +205,22 @@ def test_unsupported_arguments_are_refused(gpu_libs):
         0, 0, 0, 1.0, 1.0, 1.0, 1.0, 2, 1, False, False, True, 3, False, False, False, 100, False, False, False, True,
         None, None, None, None, None, None, None, None, None)
     assert rc == 2
+
+
+def test_pooled_buffers_do_not_leak_state_between_calls(gpu_libs):
+    """Device buffers are recycled between fit calls through the device memory pool (als.h: DevBuf): a second and a
+    third call -- the last one after cmfb200_trim_pool() handed the cache back -- must reproduce the first bit for bit,
+    for both feedback models, and so must a call of a different shape in between."""
+    dt = np.dtype(np.float32)
+    L = gpu_libs[dt]
+    m, n, k = 3000, 2000, 24
+    ixA, ixB, X = synth_coo(m, n, 60000, dt, seed=5)
+    first = fit_explicit(L, dt, ixA, ixB, X, m, n, k, niter=2)
+    other = synth_coo(500, 700, 9000, dt, seed=6, kind="counts")
+    assert fit_implicit(L, dt, *other, 500, 700, 8, niter=1)["rc"] == 0
+    second = fit_explicit(L, dt, ixA, ixB, X, m, n, k, niter=2)
+    L.cmfb200_trim_pool()
+    third = fit_explicit(L, dt, ixA, ixB, X, m, n, k, niter=2, copy_inputs=False)
+    for key in ("A", "B", "biasA", "biasB"):
+        assert np.array_equal(first[key], second[key]), key
+        assert np.array_equal(first[key], third[key]), key
