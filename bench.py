@@ -26,8 +26,23 @@ import time
 
 import numpy as np
 
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION / WARN; stdout carries exactly one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line: whatever a library prints on file descriptor 1 during the run (NCCL's version
+# banner, for one) is sent to stderr, and the line itself is written to the original descriptor at the end
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -200,6 +215,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,7 +246,7 @@ def main():
                                       preprocessing_s=r["prep_s"]),
                     e2e=dict(value=v, unit="rows/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0, sec_per_iter=r["sec_iter"])
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -461,7 +477,7 @@ def main():
                     warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype=w["dtype"], data="synthetic", config=config, sec_per_iter=ms_per_step * 1e-3,
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

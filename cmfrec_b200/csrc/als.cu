@@ -260,7 +260,7 @@ template <typename T> __global__ void scale_kernel(T *x, size_t n, T s)
 }
 
 int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
-                             real_t scale, cudaStream_t s)
+                             real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later)
 {
     cfg = c;
     stream = s;
@@ -279,6 +279,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
         cudaMemcpyAsync(dA.p, ixA, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(dB.p, ixB, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(dX.p, X, nnz * sizeof(real_t), cudaMemcpyHostToDevice, stream);
+        if (mu_later) mu = (*mu_later)();   // computed on a host thread while the copies above were in flight
         if (mu != 0 && device_subtract(dX.p, nnz, mu, stream)) return 1;
         if (scale != 1) scale_kernel<real_t><<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(dX.p, nnz, scale);
     }
@@ -503,12 +504,15 @@ int AlsState::exchange(int which)
     const int ld = solveA ? ldA : ldB;
     const int_t block = solveA ? renA.block : renB.block;
     launches += 1;
-    int rc = link->all_gather_inplace(F, (size_t)block * ld * sizeof(real_t), stream);
-    if (rc) return rc;
     const bool has_bias = !cfg.implicit && (solveA ? cfg.user_bias : cfg.item_bias);
+    // the factor block and the bias block travel in one NCCL launch
+    int rc = has_bias ? link->group_begin() : 0;
+    if (rc) return rc;
+    rc = link->all_gather_inplace(F, (size_t)block * ld * sizeof(real_t), stream);
+    if (rc == 0 && has_bias) rc = link->all_gather_inplace(solveA ? biasA.p : biasB.p, (size_t)block * sizeof(real_t), stream);
     if (has_bias) {
-        launches += 1;
-        rc = link->all_gather_inplace(solveA ? biasA.p : biasB.p, (size_t)block * sizeof(real_t), stream);
+        const int rc2 = link->group_end();
+        if (rc == 0) rc = rc2;
     }
     return rc;
 }

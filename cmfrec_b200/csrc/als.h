@@ -4,6 +4,7 @@
 // (src/collective.c:8334-8898) and fit_collective_implicit_als (src/collective.c:9827-10040) for models
 // without side information.
 #pragma once
+#include <functional>
 #include <utility>
 #include <vector>
 #include <cuda_runtime.h>
@@ -132,7 +133,7 @@ public:
     // single-GPU ingestion straight from host COO triplets: upload, subtract `mu`, multiply by `scale`, build both
     // orientations on the device (device_prep.cu).  Values are transformed as  (x - mu) * scale  in real_t.
     int setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
-                       real_t scale, cudaStream_t s);
+                       real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later = nullptr);   // mu_later: the mean is still being computed on the host; asked for once the uploads are in flight
     // starting biases computed on the device and written into the bias slots of A / B
     // which: 3 = both sides (two-sided sweeps), 1 = users only, 2 = items only
     int init_biases_on_device(int which, real_t lam_user, real_t lam_item, bool scale_lam);

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -120,9 +121,13 @@ int fit_explicit(const ExplicitArgs &a)
     // centring (src/collective.c:7555-7568 -> src/common.c:3423): mean on the host (parity-critical summation
     // order), subtraction on the device
     real_t glob_mean = 0;
-    if (a.center) glob_mean = global_mean(a.X, nnz, a.nthreads);
-    if (a.glob_mean) *a.glob_mean = glob_mean;
-    tm.lap("global mean (host)");
+    std::thread mean_thread;
+    if (a.center) mean_thread = std::thread([&]() { glob_mean = global_mean(a.X, nnz, a.nthreads); });
+    struct MeanJoiner { std::thread &t; ~MeanJoiner() { if (t.joinable()) t.join(); } } mean_joiner{mean_thread};
+    const std::function<real_t()> mean_later = [&]() {
+        if (mean_thread.joinable()) mean_thread.join();
+        return glob_mean;
+    };
 
     AlsConfig cfg;
     cfg.implicit = false;
@@ -137,9 +142,11 @@ int fit_explicit(const ExplicitArgs &a)
 
     // upload COO, centre, build CSR + CSC on the device (src/collective.c:7593 -> src/helpers.c:1375)
     AlsState st;
-    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, a.X, nnz, glob_mean, real_t(1), nullptr);
+    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, a.X, nnz, real_t(0), real_t(1), nullptr, &mean_later);
+    mean_later();
+    if (a.glob_mean) *a.glob_mean = glob_mean;
     if (rc) return rc == 2 ? refuse("this value of k") : rc;
-    tm.lap("upload COO + CSR/CSC (GPU)");
+    tm.lap("global mean (host thread) + upload COO + CSR/CSC (GPU)");
 
     // starting biases (src/collective.c:8164-8226)
     if (has_bias) {

@@ -15,6 +15,7 @@ typedef int (*CommDestroy_t)(void *);
 typedef int (*AllGather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef const char *(*GetErrorString_t)(int);
+typedef int (*Group_t)(void);
 enum { kNcclInt8 = 0, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct Api {
@@ -25,6 +26,7 @@ struct Api {
     AllGather_t AllGather = nullptr;
     AllReduce_t AllReduce = nullptr;
     GetErrorString_t GetErrorString = nullptr;
+    Group_t GroupStart = nullptr, GroupEnd = nullptr;
     bool ok = false;
 };
 
@@ -43,6 +45,8 @@ Api &api()
     a.AllGather = (AllGather_t)dlsym(a.handle, "ncclAllGather");
     a.AllReduce = (AllReduce_t)dlsym(a.handle, "ncclAllReduce");
     a.GetErrorString = (GetErrorString_t)dlsym(a.handle, "ncclGetErrorString");
+    a.GroupStart = (Group_t)dlsym(a.handle, "ncclGroupStart");
+    a.GroupEnd = (Group_t)dlsym(a.handle, "ncclGroupEnd");
     a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce;
     return a;
 }
@@ -105,6 +109,18 @@ int NcclLink::all_gather_inplace(void *base, size_t bytes_per_rank, cudaStream_t
     Api &a = api();
     const char *send = (const char *)base + (size_t)rank * bytes_per_rank;
     return check(a.AllGather(send, base, bytes_per_rank, kNcclInt8, comm, stream), "ncclAllGather");
+}
+
+// calls between group_begin() and group_end() are fused into one NCCL launch (no-ops when the symbols are missing)
+int NcclLink::group_begin()
+{
+    Api &a = api();
+    return a.GroupStart ? check(a.GroupStart(), "ncclGroupStart") : 0;
+}
+int NcclLink::group_end()
+{
+    Api &a = api();
+    return a.GroupEnd ? check(a.GroupEnd(), "ncclGroupEnd") : 0;
 }
 
 int NcclLink::all_reduce_sum(void *buf, size_t count, bool is_double, cudaStream_t stream)

@@ -16,6 +16,8 @@ public:
     // every rank contributes `bytes_per_rank` bytes located at base + rank*bytes_per_rank
     int all_gather_inplace(void *base, size_t bytes_per_rank, cudaStream_t stream);
     int all_reduce_sum(void *buf, size_t count, bool is_double, cudaStream_t stream);
+    int group_begin();   // collectives issued until group_end() go out as one NCCL launch
+    int group_end();
     int rank = 0, world = 1;
 private:
     void *comm = nullptr;
