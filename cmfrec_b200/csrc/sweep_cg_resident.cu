@@ -565,10 +565,11 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     if (mode == 1) {
         // one warp per row as in the direct kernel, the first cap1 entries of every row resident, the rest streamed;
         // rows of >= 1024 entries get a thread block, rows of >= 8192 a cluster of 8
-        nC8 = use_clusters ? count_gt(deg, n_rows, 8191) : 0;
+        static const int t_cluster = env_int("CMFB200_RES_T_CLUSTER", 8192), t_block = env_int("CMFB200_RES_T_BLOCK", 1024);
+        nC8 = use_clusters ? count_gt(deg, n_rows, t_cluster - 1) : 0;
         nC4 = nC2 = nC8;
         rp.b8 = nC8;
-        rp.b4 = rp.b2 = rp.b1 = std::max(rp.b8, count_gt(deg, n_rows, 1023));
+        rp.b4 = rp.b2 = rp.b1 = std::max(rp.b8, count_gt(deg, n_rows, t_block - 1));
     } else {
         rp.b8 = nC2;
         rp.b4 = std::max(rp.b8, count_gt(deg, n_rows, (long long)4 * cap1));
