@@ -379,8 +379,10 @@ __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSwee
         if (row0 >= 0) {
             const int nnz = (int)(end0 - beg0);
             if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+#ifdef CMF_RES_TEAMS   // 2- and 4-warp teams (CMFB200_RES_MODE=0, measured slower): compiled on request only
             else if (slot < rp.s4) resident_row<T, C, L, MODEL, GRAM_SMEM, 4>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
             else if (slot < rp.s2) resident_row<T, C, L, MODEL, GRAM_SMEM, 2>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+#endif
             else resident_row<T, C, L, MODEL, GRAM_SMEM, 1>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
         }
         row0 = row1;
@@ -527,7 +529,11 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     // mode 1 (default, measured fastest): one warp per row with a shared-memory cache; mode 0: teams sized so that
     // whole rows are resident (1-8 warps, clusters of 2-8 blocks) -- fewer L2 reads but the per-pass team overhead
     // costs more instructions than the gathers it saves (profiles/README.md)
+#ifdef CMF_RES_TEAMS
     const int mode = env_int("CMFB200_RES_MODE", 1);
+#else
+    const int mode = 1;   // the team variant is not compiled in (make EXTRA=-DCMF_RES_TEAMS)
+#endif
     const size_t fixed1 = (size_t)kW * SM::STRIPE * sizeof(T);
     size_t gram_bytes = MODEL != kModelExplicit ? (size_t)p.kk * Lay::KP * sizeof(T) : 0;
     // The constant matrix goes to shared memory whenever it fits (every row reads all of it on every pass); what is
@@ -648,15 +654,27 @@ template <int MODEL> int dispatch_resident(const CgSweepParams &p, cudaStream_t 
 
 }  // namespace
 
+// One translation unit per model (the Makefile compiles this file three times with -DCMF_RES_MODEL=0|1|2: the
+// instantiations of one model take minutes to compile); sweep_cg_dispatch.cu routes to them.
 // 0 = launched, 3 = this shape is not covered (nothing was launched: use the direct kernel), other = error
-int launch_explicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+#ifndef CMF_RES_MODEL
+#error "compile with -DCMF_RES_MODEL=0 (explicit), 1 (implicit) or 2 (collective)"
+#endif
+#if CMF_RES_MODEL == 0
+int resident_sweep_explicit(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
 {
-    return (p.gram || p.qvec || p.solve_all_rows) ? dispatch_resident<kModelCollective>(p, stream, n_launches)
-                                                  : dispatch_resident<kModelExplicit>(p, stream, n_launches);
+    return dispatch_resident<kModelExplicit>(p, stream, n_launches);
 }
-int launch_implicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+#elif CMF_RES_MODEL == 1
+int resident_sweep_implicit(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
 {
     return dispatch_resident<kModelImplicit>(p, stream, n_launches);
 }
+#else
+int resident_sweep_collective(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
+{
+    return dispatch_resident<kModelCollective>(p, stream, n_launches);
+}
+#endif
 
 }  // namespace cmfb200

@@ -206,21 +206,19 @@ def test_fp32_accuracy_is_the_references(gpu_libs, k, implicit):
     assert e_gpu <= 3 * e_ref + 1e-6, (e_gpu, e_ref)
 
 
-@pytest.mark.parametrize("path", ["panel", "panel_cl4", "resident", "teams", "direct"])
+@pytest.mark.parametrize("path", ["panel", "panel_cl4", "resident", "direct"])
 @pytest.mark.parametrize("dtype,k", [(np.float32, 64), (np.float32, 20), (np.float32, 128), (np.float64, 16), (np.float64, 64)])
 @pytest.mark.parametrize("implicit", [False, True])
 def test_every_team_size(gpu_libs, monkeypatch, path, dtype, k, implicit):
     """Row lengths from 0 to 7000 stored entries through the CG half-sweep variants: "panel" (default,
     sweep_cg_panel.cu: whole rows resident in shared memory, teams of 1-8 warps and clusters of 2-16 thread blocks;
     "panel_cl4" caps the cluster size at 4 so that the longest rows take its direct-kernel leg), "resident" (one
-    warp per row with a shared-memory cache of the gathered rows, blocks / clusters for long rows), "teams"
-    (CMFB200_RES_MODE=0: 1/2/4/8-warp teams and clusters of 2/4/8 thread blocks sized so that whole rows are resident)
-    and "direct" (CMFB200_RESIDENT=0: every pass gathers from L2).  Every row must match the reference's
+    warp per row with a shared-memory cache of the gathered rows, blocks / clusters for long rows; its 2- and 4-warp
+    team variant is compiled on request only, make EXTRA=-DCMF_RES_TEAMS) and "direct" (CMFB200_RESIDENT=0: every pass gathers from L2).  Every row must match the reference's
     optimizeA / optimizeA_implicit."""
     monkeypatch.setenv("CMFB200_PANEL", "1" if path.startswith("panel") else "0")
     monkeypatch.setenv("CMFB200_PANEL_MAXCL", "4" if path == "panel_cl4" else "16")
     monkeypatch.setenv("CMFB200_RESIDENT", "0" if path == "direct" else "1")
-    monkeypatch.setenv("CMFB200_RES_MODE", "0" if path == "teams" else "1")
     dt = np.dtype(dtype)
     L, R = gpu_libs[dt], _need_ref(dt)
     degs = [1, 2, 7, 20, 33, 47, 48, 49, 64, 90, 97, 130, 190, 200, 260, 385, 400, 500, 770, 800, 1100, 1500, 1700, 2500,
