@@ -222,35 +222,28 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
 // processing order / bucket boundaries of a side whose ptr array is already on the device (single GPU, identity numbering)
 static int plan_side_from_device(DeviceSide &side, int_t rows, cudaStream_t stream)
 {
-    std::vector<size_t> hptr((size_t)rows + 1);
-    if (cudaMemcpyAsync(hptr.data(), side.ptr.p, hptr.size() * sizeof(size_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess)
-        return 1;
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
     side.rows_padded = rows;
     side.block = rows;
     side.row_begin = 0;
     side.row_end = rows;
-    side.nnz_local = hptr[rows];
-    std::vector<int_t> order(rows);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int_t a, int_t b) {
-        return (hptr[a + 1] - hptr[a]) > (hptr[b + 1] - hptr[b]);
-    });
+    side.n_order = rows;
+    if (!side.order.alloc(std::max<size_t>((size_t)rows, 1))) return 1;
+    // the degree sort runs on the device (stable radix sort: ties keep increasing row order, like std::stable_sort);
+    // only the sorted counts come back, for the bucket boundaries
+    size_t total = 0;
+    if (int rc = device_degree_order(side.ptr.p, rows, side.order.p, side.deg_sorted, &total, stream)) return rc;
+    side.nnz_local = total;
+    const std::vector<int_t> &deg = side.deg_sorted;
     auto count_ge = [&](size_t thr, int_t limit) {
         int_t c = 0;
-        while (c < limit && hptr[order[c] + 1] - hptr[order[c]] >= thr) c++;
+        while (c < limit && (size_t)deg[c] >= thr) c++;
         return c;
     };
-    side.n_order = rows;
-    side.deg_sorted.resize(rows);
-    for (int_t i = 0; i < rows; i++) side.deg_sorted[i] = (int_t)(hptr[order[i] + 1] - hptr[order[i]]);
     side.n_long = count_ge((size_t)long_row_threshold(), rows);
     side.n_huge = count_ge((size_t)env_or("CMFB200_HUGE_ROW", 8192), side.n_long);
     side.n_big = count_ge((size_t)env_or("CMFB200_T_BIG", 512), rows);
     side.n_mid = count_ge((size_t)env_or("CMFB200_T_MID", 96), rows);
-    if (!side.order.alloc(std::max<size_t>(order.size(), 1))) return 1;
-    if (rows) cudaMemcpyAsync(side.order.p, order.data(), order.size() * sizeof(int_t), cudaMemcpyHostToDevice, stream);
-    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+    return 0;
 }
 
 template <typename T> __global__ void scale_kernel(T *x, size_t n, T s)

@@ -167,6 +167,40 @@ int device_subtract(real_t *d_x, size_t n, real_t mu, cudaStream_t stream)
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+namespace {
+__global__ void degree_kernel(const size_t *__restrict__ ptr, int_t rows, uint32_t *__restrict__ deg, int_t *__restrict__ ids)
+{
+    const int_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        deg[i] = (uint32_t)(ptr[i + 1] - ptr[i]);
+        ids[i] = i;
+    }
+}
+}  // namespace
+
+// rows sorted by decreasing number of stored entries, ties in increasing row order (a stable sort, as the host
+// version in als.cu): d_order on the device, the sorted counts and the total on the host
+int device_degree_order(const size_t *d_ptr, int_t rows, int_t *d_order, std::vector<int_t> &deg_sorted, size_t *nnz_total,
+                        cudaStream_t stream)
+{
+    deg_sorted.assign((size_t)rows, 0);
+    if (cudaMemcpyAsync(nnz_total, d_ptr + rows, sizeof(size_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    if (rows < 1) return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+    DevBuf<uint32_t> deg_in, deg_out;
+    DevBuf<int_t> ids;
+    if (!deg_in.alloc(rows) || !deg_out.alloc(rows) || !ids.alloc(rows)) return 1;
+    degree_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(d_ptr, rows, deg_in.p, ids.p);
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, deg_in.p, deg_out.p, ids.p, d_order, (int)rows, 0, 32, stream);
+    DevBuf<unsigned char> tmp;
+    if (!tmp.alloc(bytes ? bytes : 1)) return 1;
+    cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, deg_in.p, deg_out.p, ids.p, d_order, (int)rows, 0, 32, stream);
+    static_assert(sizeof(int_t) == sizeof(uint32_t), "the counts are downloaded as they are");
+    if (cudaMemcpyAsync(deg_sorted.data(), deg_out.p, (size_t)rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+        return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int device_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
                                 const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, real_t lam_user, real_t lam_item,
                                 bool scale_lam, real_t *d_biasA, real_t *d_biasB, cudaStream_t stream)
