@@ -21,6 +21,10 @@
 #include <cstdint>
 #include <cstdlib>
 
+#ifndef CMF_RES_DEPTH
+#define CMF_RES_DEPTH 4   // steps the streamed gathers run ahead of the arithmetic (8-lane layouts)
+#endif
+
 namespace cmfb200 {
 
 namespace {
@@ -211,7 +215,7 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     // Entries beyond the resident part, 32 at a time.  The gathers run D steps ahead of the arithmetic (D rotating
     // register buffers, no load issued twice) and the (column, value) pairs of the next chunk are fetched while the
     // current one is processed: the streamed part is bound by L2 latency, i.e. by the bytes in flight per warp.
-    static constexpr int D = (C <= 8 && L >= 4) ? 4 : 2;
+    static constexpr int D = (C <= 8 && L >= 4) ? (CMF_RES_DEPTH < L ? CMF_RES_DEPTH : L) : 2;
     template <int KIND, bool FULLW>
     __device__ __forceinline__ void pass_streamed(const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
     {
