@@ -132,15 +132,6 @@ static int build_side(const size_t *ptr, const int_t *idx, const real_t *val, co
         while (h < n_long && hptr[order[h] + 1] - hptr[order[h]] >= t_huge) h++;
         side.n_huge = h;
     }
-    {
-        const size_t t_big = (size_t)env_or("CMFB200_T_BIG", 512), t_mid = (size_t)env_or("CMFB200_T_MID", 96);
-        int_t a = 0, b = 0;
-        while (a < (int_t)order.size() && hptr[order[a] + 1] - hptr[order[a]] >= t_big) a++;
-        b = a;
-        while (b < (int_t)order.size() && hptr[order[b] + 1] - hptr[order[b]] >= t_mid) b++;
-        side.n_big = a;
-        side.n_mid = b;
-    }
 
     if (!side.ptr.alloc(hptr.size()) || !side.idx.alloc(std::max<size_t>(total, 1)) ||
         !side.val.alloc(std::max<size_t>(total, 1)) || !side.order.alloc(std::max<size_t>(order.size(), 1)))
@@ -189,6 +180,7 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
 {
     cfg = c;
     stream = s;
+    use_resident = env_or("CMFB200_RESIDENT", 1) != 0;   // read once per state, not per half-sweep
     if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
     cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
@@ -241,8 +233,6 @@ static int plan_side_from_device(DeviceSide &side, int_t rows, cudaStream_t stre
     };
     side.n_long = count_ge((size_t)long_row_threshold(), rows);
     side.n_huge = count_ge((size_t)env_or("CMFB200_HUGE_ROW", 8192), side.n_long);
-    side.n_big = count_ge((size_t)env_or("CMFB200_T_BIG", 512), rows);
-    side.n_mid = count_ge((size_t)env_or("CMFB200_T_MID", 96), rows);
     return 0;
 }
 
@@ -257,6 +247,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
 {
     cfg = c;
     stream = s;
+    use_resident = env_or("CMFB200_RESIDENT", 1) != 0;
     if (cfg.world != 1) return 2;
     if (cfg.kk < 1 || cfg.kk > max_supported_k()) return 2;
     if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
@@ -445,23 +436,12 @@ int AlsState::half_sweep(int which, int iter, int solver)
     }
     if (solver == 0) {
         rc = 3;
-        // opt-in: whole rows resident in shared memory across the CG passes, teams and clusters (sweep_cg_panel.cu);
-        // parity-green but slower than the cached kernel below on the measured shapes (profiles/README.md)
-        if (env_or("CMFB200_PANEL", 0)) {
-            int nl = 0;
-            rc = cfg.implicit ? launch_implicit_cg_sweep_panel(p, stream, &nl) : launch_explicit_cg_sweep_panel(p, stream, &nl);
-            if (rc == 0) launches += nl - 1;
-        }
         // default: one warp per row (a thread block / a cluster of 8 for long rows), the first entries of every share
         // cached in shared memory, the rest streamed through a pipelined gather (sweep_cg_resident.cu)
-        if (rc == 3 && env_or("CMFB200_RESIDENT", 1)) {
+        if (use_resident) {
             int nl = 0;
             rc = cfg.implicit ? launch_implicit_cg_sweep_resident(p, stream, &nl) : launch_explicit_cg_sweep_resident(p, stream, &nl);
             if (rc == 0) launches += nl - 1;
-        }
-        if (rc == 3 && env_or("CMFB200_STAGED", 0) && (cfg.implicit || (!p.gram && !p.qvec && !p.solve_all_rows))) {
-            rc = cfg.implicit ? launch_implicit_cg_sweep_staged(p, stream) : launch_explicit_cg_sweep_staged(p, stream);
-            if (rc == 0) launches += 2;
         }
         if (rc == 3) {
             // direct gathers from L2 on every pass (sweep_cg.cu); the longest rows go to a cluster kernel on a second stream

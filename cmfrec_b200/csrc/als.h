@@ -72,9 +72,9 @@ struct DeviceSide {
     DevBuf<real_t> val;
     DevBuf<int_t> order;
     std::vector<int_t> deg_sorted;   // host: stored entries of order[i], descending
-    int_t n_order = 0, n_long = 0, n_huge = 0, n_big = 0, n_mid = 0;
+    int_t n_order = 0, n_long = 0, n_huge = 0;
     CsrView view() const { return CsrView{ptr.p, idx.p, val.p}; }
-    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long, n_huge, n_big, n_mid, deg_sorted.empty() ? nullptr : deg_sorted.data()}; }
+    SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long, n_huge, deg_sorted.empty() ? nullptr : deg_sorted.data()}; }
 };
 
 struct Renumbering {              // old (caller) row id <-> device row id
@@ -120,6 +120,7 @@ public:
     const real_t *extraq[2] = {nullptr, nullptr};
     int extra_ldq[2] = {0, 0};
     bool extra_all_rows[2] = {false, false};
+    bool use_resident = true;     // CMFB200_RESIDENT=0 selects the direct-gather CG kernel (read when the state is set up)
     long long launches = 0;       // kernels launched so far (for bench.py's gpu_launches)
     // optional per-launch timing of the row-solve kernel (CUDA events on `stream`, resolved on demand)
     bool profile = false;

@@ -29,6 +29,16 @@ __global__ void histogram_kernel(const int_t *__restrict__ major, size_t nnz, un
     if (i < nnz) atomicAdd(&counts[major[i]], 1ULL);
 }
 
+// any index outside [0, limit) raises the flag (the compression below would write out of bounds / mis-sort it)
+__global__ void index_range_kernel(const int_t *__restrict__ ix, size_t nnz, int_t limit, int *__restrict__ flag)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) {
+        const int_t v = ix[i];
+        if (v < 0 || v >= limit) *flag = 1;
+    }
+}
+
 template <typename T>
 __global__ void gather_kernel(const uint32_t *__restrict__ perm, const int_t *__restrict__ minor, const T *__restrict__ val,
                               size_t nnz, int_t *__restrict__ out_idx, T *__restrict__ out_val)
@@ -130,7 +140,27 @@ int device_compress(const int_t *d_major, const int_t *d_minor, const real_t *d_
                     size_t *d_ptr, int_t *d_idx, real_t *d_out, cudaStream_t stream)
 {
     const int threads = 256;
+    // entry positions are carried as 32-bit integers through the sort: more entries than that is refused loudly
+    // (the reference takes a size_t count; a silent truncation here would build a corrupt matrix)
+    if (nnz > (size_t)0x7fffffff) {
+        std::fprintf(stderr, "cmfrec_b200: more than 2^31-1 stored entries per device are not supported.\n");
+        return 2;
+    }
     const unsigned blocks = (unsigned)((nnz + threads - 1) / threads);
+    if (nnz) {
+        DevBuf<int> flag;
+        if (!flag.alloc(1)) return 1;
+        cudaMemsetAsync(flag.p, 0, sizeof(int), stream);
+        index_range_kernel<<<blocks, threads, 0, stream>>>(d_major, nnz, nmajor, flag.p);
+        int bad = 0;
+        if (cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess)
+            return 1;
+        if (bad) {
+            std::fprintf(stderr, "cmfrec_b200: row / column index outside of [0, %d).\n", (int)nmajor);
+            return 2;
+        }
+    }
     // row pointers
     DevBuf<unsigned long long> counts;
     if (!counts.alloc((size_t)nmajor + 1)) return 1;

@@ -56,10 +56,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // [0,14) start address >> 4, [16,30) leading byte offset >> 4 (not used by swizzled K-major layouts: 1), [32,46)
 // stride byte offset >> 4 (between groups of 8 M / N rows), [46,48) version = 1, [61,64) layout type = 2
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+// `layout`: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout MN-major tf32 operands admit:
+// atoms of 32 MN elements x 4 K, 128 bytes per K row, the 32-byte chunks of a row XOR-ed with the K index mod 4;
+// LBO = stride between MN atoms, SBO = stride between K atoms)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -96,6 +99,7 @@ template <int LD> struct GramTc {
     static constexpr uint32_t SBO = 1024;                // between groups of 8 columns of G (8 atom rows x 128 bytes)
     static constexpr uint32_t KATOM = (LD / 8) * SBO;    // between groups of 32 rows of G
     static constexpr uint32_t PART_BYTES = (uint32_t)KT * LD * 4;
+    static constexpr uint32_t MN_LBO = (uint32_t)KT * 128u;  // MN-major staging: between atoms of 32 columns of G
     static constexpr uint32_t STAGE_BYTES = 2 * PART_BYTES;  // HI then LO
     static constexpr int M = LD >= 128 ? 128 : 64;
     static constexpr int MT = LD / M;                    // accumulator tiles stacked along M (2 at LD = 256)
@@ -111,7 +115,10 @@ template <int LD> struct GramTc {
     static constexpr size_t SMEM_BYTES = 2 * (size_t)STAGE_BYTES + 1024;   // + alignment slack
 };
 
-template <int LD>
+// MNMAJOR = true: the tile goes to shared memory UNtransposed (rows of G = K rows of 128-byte MN atoms, 16-byte vector
+// stores, a quarter-warp fills one whole 128-byte row) and the tensor core reads it as an MN-major operand in the
+// SWIZZLE_128B_BASE32B layout; false: transposed to K-major SWIZZLE_128B with 4-byte stores (round-1 path).
+template <int LD, bool MNMAJOR>
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, float *__restrict__ partial)
 {
@@ -155,8 +162,9 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
 #pragma unroll
         for (int i = 0; i < S::PER_THREAD; i++) {
             const int c = tid + i * kGramThreads;
-            const long long r = r0 + c % S::KT;
-            buf[i] = r < r_end ? __ldg(reinterpret_cast<const float4 *>(G + (size_t)r * LD) + (c / S::KT)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const long long r = r0 + (MNMAJOR ? c / S::CHUNKS : c % S::KT);
+            const int j = MNMAJOR ? c % S::CHUNKS : c / S::KT;
+            buf[i] = r < r_end ? __ldg(reinterpret_cast<const float4 *>(G + (size_t)r * LD) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     // element (column mn of G, row k of the tile) -> K-major swizzled position
@@ -166,8 +174,23 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
 #pragma unroll
         for (int i = 0; i < S::PER_THREAD; i++) {
             const int c = tid + i * kGramThreads;
-            const int k = c % S::KT, j = c / S::KT;
+            const int k = MNMAJOR ? c / S::CHUNKS : c % S::KT, j = MNMAJOR ? c % S::CHUNKS : c / S::KT;
             const float x[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
+            if constexpr (MNMAJOR) {
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    uint32_t hb;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[e]));
+                    h[e] = __uint_as_float(hb);
+                    l[e] = x[e] - h[e];
+                }
+                const uint32_t off = (uint32_t)(j >> 3) * S::MN_LBO + (uint32_t)k * 128u + (uint32_t)((((j >> 1) & 3) ^ (k & 3)) << 5) +
+                                     (uint32_t)(j & 1) * 16u;
+                *reinterpret_cast<float4 *>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4 *>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                continue;
+            }
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int mn = 4 * j + e;
@@ -197,16 +220,18 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
 #pragma unroll 1
             for (int k8 = 0; k8 < S::KT / 8; k8++) {
                 // 8 rows of G = 32 bytes along an atom row; 4 such slices per atom, then the next group of 32 rows
-                const uint32_t koff = (uint32_t)(k8 >> 2) * S::KATOM + (uint32_t)(k8 & 3) * 32u;
-                const uint64_t b_hi = make_desc(hi + koff, 16, S::SBO), b_lo = make_desc(lo + koff, 16, S::SBO);
+                const uint32_t koff = MNMAJOR ? (uint32_t)k8 * 1024u : (uint32_t)(k8 >> 2) * S::KATOM + (uint32_t)(k8 & 3) * 32u;
+                const uint32_t lbo = MNMAJOR ? S::MN_LBO : 16u, sbo = MNMAJOR ? 512u : S::SBO, lay = MNMAJOR ? 1u : 2u;
+                const uint32_t idesc = MNMAJOR ? (S::IDESC | (1u << 15) | (1u << 16)) : S::IDESC;
+                const uint64_t b_hi = make_desc(hi + koff, lbo, sbo, lay), b_lo = make_desc(lo + koff, lbo, sbo, lay);
 #pragma unroll
                 for (int mt = 0; mt < S::MT; mt++) {
-                    const uint32_t a_off = koff + (uint32_t)mt * (S::M / 8) * S::SBO;
-                    const uint64_t a_hi = make_desc(hi + a_off, 16, S::SBO), a_lo = make_desc(lo + a_off, 16, S::SBO);
+                    const uint32_t a_off = koff + (MNMAJOR ? (uint32_t)mt * (S::M / 32) * S::MN_LBO : (uint32_t)mt * (S::M / 8) * S::SBO);
+                    const uint64_t a_hi = make_desc(hi + a_off, lbo, sbo, lay), a_lo = make_desc(lo + a_off, lbo, sbo, lay);
                     const uint32_t d = tmem_base + (uint32_t)((t % S::NACC) * S::MT * S::N + mt * S::N);
-                    umma_tf32(d, a_hi, b_hi, S::IDESC, (t >= S::NACC || k8 > 0) ? 1u : 0u);
-                    umma_tf32(d, a_hi, b_lo, S::IDESC, 1u);
-                    umma_tf32(d, a_lo, b_hi, S::IDESC, 1u);
+                    umma_tf32(d, a_hi, b_hi, idesc, (t >= S::NACC || k8 > 0) ? 1u : 0u);
+                    umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                    umma_tf32(d, a_lo, b_hi, idesc, 1u);
                 }
             }
             umma_commit(&mma_done[stage]);   // implies tcgen05.fence::before_thread_sync
@@ -266,7 +291,8 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
 template <int LD> int launch_gram_tc_ld(const float *G, int_t rows, int kk, int nslices, float *partial, cudaStream_t stream)
 {
     typedef GramTc<LD> S;
-    auto kern = gram_tc_kernel<LD>;
+    static const bool mn_major = [] { const char *e = std::getenv("CMFB200_GRAM_MN"); return e ? std::atoi(e) != 0 : false; }();
+    auto kern = mn_major ? gram_tc_kernel<LD, true> : gram_tc_kernel<LD, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES) != cudaSuccess) return 1;
     kern<<<nslices, kGramThreads, S::SMEM_BYTES, stream>>>(G, rows, kk, nslices, partial);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -22,7 +22,6 @@ struct SweepPlan {          // device pointers, built once per CSR by build_swee
     int_t n_rows;           // length of order
     int_t n_long;           // the first n_long rows of order get one whole thread block each
     int_t n_huge;           // the first n_huge (<= n_long) rows get a whole cluster of thread blocks each
-    int_t n_big, n_mid;     // staged kernel: rows [0,n_big) -> 16-warp teams, [n_big,n_mid) -> 4-warp teams, rest 1 warp
     const int_t *host_deg;  // HOST copy of the stored-entry counts of `order` (descending); null = not available
 };
 
@@ -51,22 +50,11 @@ struct CgSweepParams {
 int launch_explicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream);
 int launch_implicit_cg_sweep(const CgSweepParams &p, cudaStream_t stream);
 
-// Same sweeps with the gathered rows staged in shared memory by bulk async copies (sweep_cg_staged.cu).
-// Return 3 when the shape is not covered (nothing was launched): use the direct variant above.
-int launch_explicit_cg_sweep_staged(const CgSweepParams &p, cudaStream_t stream);
-int launch_implicit_cg_sweep_staged(const CgSweepParams &p, cudaStream_t stream);
-
 // Same sweeps with every row's gathered block resident in shared memory across the CG passes, teams of 1-8 warps
 // or clusters of 2-8 thread blocks per row (sweep_cg_resident.cu).  Return 3 when the shape is not covered.
 // *n_launches (optional) is incremented by the number of kernels launched.
 int launch_explicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
 int launch_implicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
-
-// Panel variant (sweep_cg_panel.cu): the gathered rows resident in shared memory, predicate-free pipelined passes,
-// transposed reductions, distributed CG algebra, run-time team sizes, clusters of 2-16 thread blocks for long rows.
-// Return 3 when the shape is not covered.
-int launch_explicit_cg_sweep_panel(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
-int launch_implicit_cg_sweep_panel(const CgSweepParams &p, cudaStream_t stream, int *n_launches);
 
 // Exact per-row solves (normal equations + Cholesky); same parameter block, `max_cg_steps` and
 // `bias_start_one` only matter for rows without entries.  reference: factors_closed_form sparse branch

@@ -206,18 +206,14 @@ def test_fp32_accuracy_is_the_references(gpu_libs, k, implicit):
     assert e_gpu <= 3 * e_ref + 1e-6, (e_gpu, e_ref)
 
 
-@pytest.mark.parametrize("path", ["panel", "panel_cl4", "resident", "direct"])
+@pytest.mark.parametrize("path", ["resident", "direct"])
 @pytest.mark.parametrize("dtype,k", [(np.float32, 64), (np.float32, 20), (np.float32, 128), (np.float64, 16), (np.float64, 64)])
 @pytest.mark.parametrize("implicit", [False, True])
 def test_every_team_size(gpu_libs, monkeypatch, path, dtype, k, implicit):
-    """Row lengths from 0 to 7000 stored entries through the CG half-sweep variants: "panel" (default,
-    sweep_cg_panel.cu: whole rows resident in shared memory, teams of 1-8 warps and clusters of 2-16 thread blocks;
-    "panel_cl4" caps the cluster size at 4 so that the longest rows take its direct-kernel leg), "resident" (one
-    warp per row with a shared-memory cache of the gathered rows, blocks / clusters for long rows; its 2- and 4-warp
-    team variant is compiled on request only, make EXTRA=-DCMF_RES_TEAMS) and "direct" (CMFB200_RESIDENT=0: every pass gathers from L2).  Every row must match the reference's
+    """Row lengths from 0 to 7000 stored entries through the CG half-sweep variants: "resident" (default: one warp per
+    row with a shared-memory cache of the gathered rows, thread blocks / clusters for long rows) and "direct"
+    (CMFB200_RESIDENT=0: every pass gathers from L2; also what serves k > 256).  Every row must match the reference's
     optimizeA / optimizeA_implicit."""
-    monkeypatch.setenv("CMFB200_PANEL", "1" if path.startswith("panel") else "0")
-    monkeypatch.setenv("CMFB200_PANEL_MAXCL", "4" if path == "panel_cl4" else "16")
     monkeypatch.setenv("CMFB200_RESIDENT", "0" if path == "direct" else "1")
     dt = np.dtype(dtype)
     L, R = gpu_libs[dt], _need_ref(dt)
@@ -277,9 +273,23 @@ def test_every_team_size(gpu_libs, monkeypatch, path, dtype, k, implicit):
     scale = np.abs(T).max()
     e_gpu = np.abs(got - T).max(axis=1) / scale
     e_ref = np.abs(want - T).max(axis=1) / scale
-    # a row whose ||r||^2 lands next to one of the CG's absolute exit thresholds may take one step more or less than the
-    # reference (1e-2 apart in float32): allowed on a minority of rows, and never further than that
-    # (how many rows flip depends on the last bits of the Gram as well: 10 of 60 with the FMA Gram, 11 with the
-    # tensor-core one on the k = 128 implicit case)
-    bad = np.nonzero(e_gpu > np.maximum(3 * e_ref, 1e-3))[0]
-    assert bad.size <= m // 5 and e_gpu.max() <= 5e-2, [(int(r), degs[r % len(degs)], float(e_gpu[r]), float(e_ref[r])) for r in bad]
+    # Row by row: no further from exact arithmetic than 3x the reference's own float32 error (floor 1e-3).  The only
+    # admissible exceptions are rows whose ||r||^2 (float64 trace of the same solve) lands next to one of the CG's
+    # absolute exit thresholds, where a float32 run can take one step more or fewer than the reference: each exception
+    # is verified against that trace, and is never further than 5e-2.
+    from support import cg_residual_trace, near_cg_threshold
+    bad = np.nonzero(~(e_gpu <= np.maximum(3 * e_ref, 1e-3)))[0]
+    unexplained = []
+    for r in bad:
+        beg, end = int(csr[0][r]), int(csr[0][r + 1])
+        cols = csr[1][beg:end]
+        if implicit:
+            Bd = B0.astype(np.float64)
+            tr = cg_residual_trace(Bd[cols], csr[2][beg:end], A0[r], np.full(k, lam), 3, BtB=Bd.T @ Bd)
+        else:
+            Gd = np.concatenate([B0[cols].astype(np.float64), np.ones((cols.size, 1))], 1)
+            tr = cg_residual_trace(Gd, Xc[beg:end], np.append(A0[r], 1.0), np.append(np.full(k, lam), 3.0), 3)
+        if not near_cg_threshold(tr):
+            unexplained.append((int(r), degs[r % len(degs)], float(e_gpu[r]), float(e_ref[r]), tr))
+    assert not unexplained, unexplained
+    assert np.isfinite(e_gpu).all() and e_gpu.max() <= 5e-2, float(e_gpu.max())
