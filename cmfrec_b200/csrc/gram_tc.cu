@@ -291,7 +291,7 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
 template <int LD> int launch_gram_tc_ld(const float *G, int_t rows, int kk, int nslices, float *partial, cudaStream_t stream)
 {
     typedef GramTc<LD> S;
-    static const bool mn_major = [] { const char *e = std::getenv("CMFB200_GRAM_MN"); return e ? std::atoi(e) != 0 : false; }();
+    static const bool mn_major = [] { const char *e = std::getenv("CMFB200_GRAM_MN"); return e ? std::atoi(e) != 0 : true; }();   // default since round 2: verified on B200 by tests/test_gpu_gram.py
     auto kern = mn_major ? gram_tc_kernel<LD, true> : gram_tc_kernel<LD, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES) != cudaSuccess) return 1;
     kern<<<nslices, kGramThreads, S::SMEM_BYTES, stream>>>(G, rows, kk, nslices, partial);

@@ -164,7 +164,10 @@ def test_large_rank_implicit_fp32(gpu_libs, k, solver):
     ixA, ixB, X = synth_coo(m, n, 400000, dt, seed=k, kind="counts")
     csr = csr_csc(L, dt, ixA, ixB, X, m, n)
     rng = np.random.default_rng(k)
-    A0 = (rng.random((m, k)) * 0.1).astype(dt); B0 = (rng.random((n, k)) * 0.1).astype(dt)
+    # zero-mean factors, as after the first alternations of a fit.  (All-positive uniform factors make G^T G close to
+    # rank one at this k: condition number ~1e3, and the reference's own float32 result is then 4e-3 (median) to
+    # 6e-2 (worst row) away from exact arithmetic -- measured, tools/fp32_noise_k256.py -- which leaves nothing to test.)
+    A0 = (rng.normal(size=(m, k)) * 0.1).astype(dt); B0 = (rng.normal(size=(n, k)) * 0.1).astype(dt)
     lam = 5.0
     use_cg = solver == "cg"
     with AlsSession(L, dt, csr[:3], csr[3:], m, n, k, implicit=True, lam_A=lam, lam_B=lam) as s:
@@ -177,7 +180,7 @@ def test_large_rank_implicit_fp32(gpu_libs, k, solver):
     T = A0.astype(np.float64)
     O.optimizeA_implicit(np.float64, T, B0.astype(np.float64), csr[0], csr[1], csr[2].astype(np.float64), lam=lam,
                          use_cg=use_cg, max_cg_steps=3)
-    assert rows_match(A1, Aref, 1e-3, outlier_frac=0.005), rel_err(A1, Aref)
+    assert rows_match(A1, Aref, 2e-4, outlier_frac=0.001), rel_err(A1, Aref)      # SURVEY 8(d) T1 float32 tolerance
     _quantiles_vs_exact(A1, Aref, T, "A k=%d" % k)
 
 
