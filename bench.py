@@ -53,6 +53,8 @@ WORKLOADS = {
     "ml10m_explicit_cg_k64_f32": dict(shape="ml10m", implicit=False, k=64, dtype="f32", use_cg=True),
     "lastfm_implicit_cg_k64_f32": dict(shape="lastfm", implicit=True, k=64, dtype="f32", use_cg=True),
     "ml10m_explicit_chol_k64_f32": dict(shape="ml10m", implicit=False, k=64, dtype="f32", use_cg=False),
+    "ml10m_explicit_chol_k128_f32": dict(shape="ml10m", implicit=False, k=128, dtype="f32", use_cg=False),
+    "lastfm_implicit_chol_k64_f32": dict(shape="lastfm", implicit=True, k=64, dtype="f32", use_cg=False),
     "ml10m_explicit_cg_k128_f32": dict(shape="ml10m", implicit=False, k=128, dtype="f32", use_cg=True),
     "lastfm_implicit_cg_k128_f32": dict(shape="lastfm", implicit=True, k=128, dtype="f32", use_cg=True),
     "lastfm_implicit_cg_k256_f32": dict(shape="lastfm", implicit=True, k=256, dtype="f32", use_cg=True),

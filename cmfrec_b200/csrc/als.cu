@@ -4,6 +4,7 @@
 #include "device_prep.h"
 #include "collective.h"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -181,6 +182,7 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     cfg = c;
     stream = s;
     use_resident = env_or("CMFB200_RESIDENT", 1) != 0;   // read once per state, not per half-sweep
+    use_nm_cg = env_or("CMFB200_NMCG", 0) != 0;
     if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
     cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
@@ -207,6 +209,7 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream);
     if (cfg.implicit) {
         if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
+        if (device_all_positive(byA.val.p, byA.nnz_local, &values_positive, stream)) return 1;
     }
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
@@ -248,6 +251,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
     cfg = c;
     stream = s;
     use_resident = env_or("CMFB200_RESIDENT", 1) != 0;
+    use_nm_cg = env_or("CMFB200_NMCG", 0) != 0;
     if (cfg.world != 1) return 2;
     if (cfg.kk < 1 || cfg.kk > max_supported_k()) return 2;
     if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
@@ -288,6 +292,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
     cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream);
     if (cfg.implicit) {
         if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
+        if (device_all_positive(byA.val.p, byA.nnz_local, &values_positive, stream)) return 1;
     }
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
@@ -415,6 +420,7 @@ int AlsState::half_sweep(int which, int iter, int solver)
         launches += 2;
         if (rc) return rc;
         p.gram = gram.p;
+        p.values_positive = values_positive;
     } else {
         p.solve_bias = solveA ? cfg.user_bias : cfg.item_bias;
         p.center_opp = solveA ? cfg.item_bias : cfg.user_bias;
@@ -427,6 +433,13 @@ int AlsState::half_sweep(int which, int iter, int solver)
         p.ldq = extra_ldq[which ? 1 : 0];
         p.solve_all_rows = extra_all_rows[which ? 1 : 0];
     }
+    static DevBuf<long long> nm_dbg;
+    static const bool nm_dbg_on = env_or("CMFB200_NM_DEBUG", 0) != 0;
+    if (nm_dbg_on) {
+        if (!nm_dbg.p) nm_dbg.alloc(148 * 32);
+        cudaMemsetAsync(nm_dbg.p, 0, 148 * 32 * sizeof(long long), stream);
+        p.debug = nm_dbg.p;
+    }
     int rc;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (profile) {
@@ -436,9 +449,13 @@ int AlsState::half_sweep(int which, int iter, int solver)
     }
     if (solver == 0) {
         rc = 3;
+        // explicit / collective model up to k = 64 (fp32): every row's normal matrix from the tensor cores, the CG run on it
+        // (sweep_nm.cu) -- one gather per stored entry instead of one per CG pass
+        // (opt-in, CMFB200_NMCG=1: parity-green, but its producer warps do not yet keep up with the cached kernel below)
+        if (use_nm_cg && !cfg.implicit) rc = launch_explicit_cg_sweep_nm(p, stream);
         // default: one warp per row (a thread block / a cluster of 8 for long rows), the first entries of every share
         // cached in shared memory, the rest streamed through a pipelined gather (sweep_cg_resident.cu)
-        if (use_resident) {
+        if (rc == 3 && use_resident) {
             int nl = 0;
             rc = cfg.implicit ? launch_implicit_cg_sweep_resident(p, stream, &nl) : launch_explicit_cg_sweep_resident(p, stream, &nl);
             if (rc == 0) launches += nl - 1;
@@ -466,6 +483,18 @@ int AlsState::half_sweep(int which, int iter, int solver)
         sweep_events[which ? 1 : 0].emplace_back(e0, e1);
     }
     launches += 1;
+    if (nm_dbg_on && rc == 0) {
+        std::vector<long long> h(148 * 32);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), nm_dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int blk : {0, 1, 73, 147}) {
+            const long long *o = h.data() + (size_t)blk * 32;
+            std::fprintf(stderr, "[nm dbg] which=%d blk=%d | loaders total/wait/stages:", which, blk);
+            for (int w = 0; w < 4; w++) std::fprintf(stderr, " %lld/%lld/%lld", o[w * 3], o[w * 3 + 1], o[w * 3 + 2]);
+            std::fprintf(stderr, " | mma total/accw/fullw: %lld/%lld/%lld | asm total/accw/matw/rows: %lld/%lld/%lld/%lld | solver0 total/wait/n: %lld/%lld/%lld\n",
+                         o[12], o[13], o[14], o[16], o[17], o[18], o[19], o[20], o[21], o[22]);
+        }
+    }
     return rc;
 }
 

@@ -120,6 +120,8 @@ public:
     const real_t *extraq[2] = {nullptr, nullptr};
     int extra_ldq[2] = {0, 0};
     bool extra_all_rows[2] = {false, false};
+    bool values_positive = false;   // implicit model: every stored value is > 0 (checked once when the state is set up)
+    bool use_nm_cg = false;       // CMFB200_NMCG=1: run the explicit model's CG on the tensor-core-built normal matrix (sweep_nm.cu)
     bool use_resident = true;     // CMFB200_RESIDENT=0 selects the direct-gather CG kernel (read when the state is set up)
     long long launches = 0;       // kernels launched so far (for bench.py's gpu_launches)
     // optional per-launch timing of the row-solve kernel (CUDA events on `stream`, resolved on demand)

@@ -273,6 +273,27 @@ int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats,
 
 void cmfb200_trim_pool(void) { cmfb200::devbuf_trim_pool(); }
 
+namespace {
+__global__ void poison_smem_kernel(unsigned pattern)
+{
+    extern __shared__ unsigned poison_words[];
+    const unsigned nwords = 220u * 1024u / 4u;
+    for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) poison_words[i] = pattern;
+    __syncthreads();
+    if (poison_words[(threadIdx.x * 7u) % nwords] != pattern) __trap();   // keeps the stores alive
+}
+}  // namespace
+
+int cmfb200_debug_poison_smem(unsigned pattern)
+{
+    if (cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    poison_smem_kernel<<<sms, 256, 220 * 1024>>>(pattern);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
+}
+
 int cmfb200_als_sync(cmfb200_als *s) { return cudaStreamSynchronize(s->st.stream) == cudaSuccess ? 0 : 1; }
 
 long long cmfb200_als_launch_count(const cmfb200_als *s) { return s->st.launches; }

@@ -190,6 +190,31 @@ int device_compress(const int_t *d_major, const int_t *d_minor, const real_t *d_
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+namespace {
+__global__ void any_nonpositive_kernel(const real_t *__restrict__ x, size_t n, int *__restrict__ flag)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(x[i] > real_t(0))) *flag = 1;
+}
+}  // namespace
+
+// *all_positive = every stored value is > 0 (synchronises the stream)
+int device_all_positive(const real_t *d_x, size_t n, bool *all_positive, cudaStream_t stream)
+{
+    *all_positive = true;
+    if (!n) return 0;
+    DevBuf<int> flag;
+    if (!flag.alloc(1)) return 1;
+    cudaMemsetAsync(flag.p, 0, sizeof(int), stream);
+    any_nonpositive_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_x, n, flag.p);
+    int bad = 0;
+    if (cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+        return 1;
+    *all_positive = bad == 0;
+    return 0;
+}
+
 int device_subtract(real_t *d_x, size_t n, real_t mu, cudaStream_t stream)
 {
     if (!n) return 0;

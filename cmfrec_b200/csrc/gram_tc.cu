@@ -109,6 +109,7 @@ template <int LD> struct GramTc {
     // NACC independent accumulators, one per stage in rotation, summed with round-to-nearest adds in the epilogue.
     static constexpr int TMEM_COLS = 512;
     static constexpr int NACC = TMEM_COLS / (MT * N);    // 8, 4 or 1
+    static_assert(KT / 8 >= NACC, "every accumulator is first written during the first stage");
     // instruction descriptor (InstrDescriptor): D = f32 (bit 4), A = B = tf32 (2 at bits 7 and 10), both K-major
     // (bits 15, 16 clear), N >> 3 at bit 17, M >> 4 at bit 24
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -228,8 +229,10 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
                 for (int mt = 0; mt < S::MT; mt++) {
                     const uint32_t a_off = koff + (MNMAJOR ? (uint32_t)mt * (S::M / 32) * S::MN_LBO : (uint32_t)mt * (S::M / 8) * S::SBO);
                     const uint64_t a_hi = make_desc(hi + a_off, lbo, sbo, lay), a_lo = make_desc(lo + a_off, lbo, sbo, lay);
-                    const uint32_t d = tmem_base + (uint32_t)((t % S::NACC) * S::MT * S::N + mt * S::N);
-                    umma_tf32(d, a_hi, b_hi, idesc, (t >= S::NACC || k8 > 0) ? 1u : 0u);
+                    // accumulators rotate with the 8-row step (not with the stage): the shortest possible chains of
+                    // truncating additions, every accumulator first written in the first stage
+                    const uint32_t d = tmem_base + (uint32_t)((k8 % S::NACC) * S::MT * S::N + mt * S::N);
+                    umma_tf32(d, a_hi, b_hi, idesc, (t > 0 || k8 >= S::NACC) ? 1u : 0u);
                     umma_tf32(d, a_hi, b_lo, idesc, 1u);
                     umma_tf32(d, a_lo, b_hi, idesc, 1u);
                 }
@@ -266,7 +269,7 @@ gram_tc_kernel(const float *__restrict__ G, int_t rows, int kk, int nslices, flo
                 float sum[32];
 #pragma unroll
                 for (int e = 0; e < 32; e++) sum[e] = 0.f;
-                const int nacc = ntiles < S::NACC ? ntiles : S::NACC;
+                const int nacc = ntiles > 0 ? S::NACC : 0;      // KT / 8 >= NACC: the first stage touches all of them
                 for (int a = 0; a < nacc; a++) {   // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * S::MT * S::N + mt * S::N + c0), v);

@@ -43,6 +43,8 @@ struct CgSweepParams {
                                   // implicit model: G^T G; explicit model with side info / implicit features: Q
     const real_t *qvec; int ldq;  // explicit + side info: per-row vector [rows x ldq] added to the right-hand side
     bool solve_all_rows;          // explicit + side info: rows without stored entries are solved too
+    bool values_positive;         // implicit model: every stored value is > 0 (lets the tensor-core sweep use sqrt(x) weights)
+    void *debug;                  // developer builds (-DNM_TIMING): device buffer for per-role cycle counts, else null
     cudaStream_t side_stream;     // optional second stream for the long-row kernel (caller orders it around the sweep)
 };
 
@@ -61,6 +63,13 @@ int launch_implicit_cg_sweep_resident(const CgSweepParams &p, cudaStream_t strea
 // src/common.c:978-1013 + 1058-1070, factors_implicit_chol src/common.c:2063-2126.
 int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream);
 int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream);
+// the same with every row's normal matrix built on the tensor cores (sweep_nm.cu; fp32, padded widths 64 / 128);
+// return 3 when the shape is not covered (nothing launched).  The launchers above try these first (CMFB200_NM=0: never).
+int launch_explicit_chol_sweep_nm(const CgSweepParams &p, cudaStream_t stream);
+int launch_implicit_chol_sweep_nm(const CgSweepParams &p, cudaStream_t stream);
+// explicit / collective model, k <= 64: the reference's truncated CG run on the tensor-core-built normal matrix (one
+// gather per stored entry instead of one per CG pass); 3 = not covered
+int launch_explicit_cg_sweep_nm(const CgSweepParams &p, cudaStream_t stream);
 
 // gram[kk x kk] = G[:, :kk]^T G[:, :kk] over `rows` rows (full symmetric storage);
 // workspace must hold gram_workspace_elems(kk) elements.

@@ -13,6 +13,7 @@
 // every thread), then written to shared memory and factorised there (right-looking, two barriers per column);
 // the two triangular solves are done by one warp.  Rows without entries are left as the reference leaves them.
 #include "cg_row.cuh"
+#include <cstdlib>
 
 namespace cmfb200 {
 
@@ -333,11 +334,28 @@ template <int MODEL> int dispatch_chol(const CgSweepParams &p, cudaStream_t stre
 
 }  // namespace
 
+static bool nm_enabled()
+{
+    const char *e = std::getenv("CMFB200_NM");
+    return e ? std::atoi(e) != 0 : true;
+}
+
 int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream)
 {
+    if (nm_enabled()) {
+        const int rc = launch_explicit_chol_sweep_nm(p, stream);
+        if (rc != 3) return rc;
+    }
     return (p.gram || p.qvec || p.solve_all_rows) ? dispatch_chol<kModelCollective>(p, stream)
                                                   : dispatch_chol<kModelExplicit>(p, stream);
 }
-int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream) { return dispatch_chol<kModelImplicit>(p, stream); }
+int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream)
+{
+    if (nm_enabled()) {
+        const int rc = launch_implicit_chol_sweep_nm(p, stream);
+        if (rc != 3) return rc;
+    }
+    return dispatch_chol<kModelImplicit>(p, stream);
+}
 
 }  // namespace cmfb200

@@ -180,6 +180,9 @@ int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats,
 /* Device buffers are recycled between calls through the device's default memory pool (CMFB200_POOL=0 disables it);
  * this hands the cached memory back to the driver. */
 void cmfb200_trim_pool(void);
+/* Test aid: fills the shared memory of every SM with `pattern` (e.g. 0x7fc00000 = NaN), so that a kernel launched next
+ * that reads shared memory it never wrote produces visibly wrong results instead of depending on what ran before. */
+int cmfb200_debug_poison_smem(unsigned pattern);
 
 typedef struct cmfb200_als cmfb200_als;
 

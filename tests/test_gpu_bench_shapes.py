@@ -248,3 +248,24 @@ def test_two_gpu_fit_equals_one_gpu_fit():
     proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     sys.stdout.write(proc.stdout[-4000:])
     assert proc.returncode == 0 and "MULTI_GPU_CHECK PASS" in proc.stdout
+
+
+@pytest.mark.parametrize("k", [16, 40, 64])
+def test_tensor_core_cg_variant(gpu_libs, monkeypatch, k):
+    """CMFB200_NMCG=1: the explicit model's truncated CG run on the normal matrix the tensor cores build (sweep_nm.cu,
+    one gather per stored entry) must give the iterates of the reference's factors_explicit_cg (src/common.c:1098)."""
+    monkeypatch.setenv("CMFB200_NMCG", "1")
+    dt = np.dtype(np.float32)
+    L, R = gpu_libs[dt], _need_ref(dt)
+    m, n = 5000, 900
+    ixA, ixB, X = synth_coo(m, n, 150000, dt, seed=40 + k)
+    X = (X - X.mean()).astype(dt)
+    csr = csr_csc(L, dt, ixA, ixB, X, m, n)
+    rng = np.random.default_rng(k)
+    A0 = (rng.normal(size=(m, k)) * 0.1).astype(dt); B0 = (rng.normal(size=(n, k)) * 0.1).astype(dt)
+    bA0 = (rng.normal(size=m) * 0.3).astype(dt); bB0 = (rng.normal(size=n) * 0.3).astype(dt)
+    res = _explicit_sweeps_vs_reference(L, R, dt, csr, m, n, k, A0, bA0, B0, bB0, 0.05, True, 1, "cg", exact=True)
+    for side in ("B", "A"):
+        got, want, exact = res[side]
+        assert rows_match(got, want, 1e-3, outlier_frac=0.001), (side, rel_err(got, want))
+        _quantiles_vs_exact(got, want, exact, side)

@@ -18,6 +18,14 @@ pytestmark = pytest.mark.gpu
 TOL = {np.dtype(np.float64): 1e-9, np.dtype(np.float32): 1e-3}
 
 
+def _bad_rows(got, want, indptr, tol):
+    """(row, stored entries, first offending columns) of the rows that are not finite or off by more than tol"""
+    err = np.abs(got.astype(np.float64) - want) / max(np.abs(want).max(), 1e-300)
+    bad = np.nonzero(~(err.max(axis=1) <= tol))[0]
+    deg = np.diff(indptr).astype(int)
+    return [(int(r), int(deg[r]), np.nonzero(~(err[r] <= tol))[0][:6].tolist()) for r in bad[:12]], int(bad.size)
+
+
 def _need_ref(dt):
     R = ref(dt)
     if R is None:
@@ -108,7 +116,7 @@ def test_explicit_half_sweeps(gpu_libs, dtype, k, solver, biases, scale_lam):
     Bref = Bsol[:, :k]
     bBref = Bsol[:, k] if item_bias else None
     tol = TOL[dt]
-    assert rows_match(B1, Bref, tol), rel_err(B1, Bref)
+    assert rows_match(B1, Bref, tol), (rel_err(B1, Bref), _bad_rows(B1, Bref, csr[3], tol))
     if item_bias:
         assert rows_match(bB1[:, None], bBref[:, None], tol * max(1.0, np.abs(Bref).max() / np.abs(bBref).max()))
 
