@@ -427,42 +427,44 @@ def main():
                        seconds=t_e2e, iterations=K,
                        what="one fit_collective_%s_als call, pinned host buffers in / out" % ("implicit" if w["implicit"] else "explicit"))
         else:
-            # N > 1: the reference-named entry points take no communicator, so the public call here is the building-block
-            # API one level below them (include/cmfrec_b200.h PART 2) on host buffers: create (partition + upload of this
-            # rank's CSR / CSC blocks), upload of the initial factors, K iterations with their all-gathers, download.
+            # N > 1: the SAME reference-named entry point on every rank after cmfb200_set_world (rank, world, NCCL id):
+            # every rank passes the full COO triplets from pinned host memory and receives the full factors; ingestion
+            # (CSR / CSC, centring, biases), the dealing of the rows to the ranks, K iterations with their all-gathers and
+            # the download are all inside the timed region
             assert not (w.get("side") or w.get("implicit_features"))
-            outA = np.zeros((m, w["k"]), dt); outB = np.zeros((n, w["k"]), dt)
-            obA = np.zeros(m, dt) if bA is not None else None
-            obB = np.zeros(n, dt) if bB is not None else None
-
-            def run_blocks(nit):
-                h2 = C.c_void_p()      # same communicator id as above: the library reuses the communicator
-                assert L.cmfb200_als_create(C.byref(h2), C.byref(opt), *[ptr(t) for t in csr]) == 0
-                assert L.cmfb200_als_set_factors(h2, ptr(A0), ptr(bA), ptr(B0), ptr(bB)) == 0
-                assert L.cmfb200_als_iterate(h2, 0, nit, 1 << 30, use_cg, 0) == 0
-                assert L.cmfb200_als_get_factors(h2, ptr(outA), ptr(obA), ptr(outB), ptr(obB)) == 0
-                nzA, nzB, rA, rB = C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_int(0)
-                L.cmfb200_als_local_counts(h2, C.byref(nzA), C.byref(nzB), C.byref(rA), C.byref(rB))
-                L.cmfb200_als_destroy(h2)
-                return nzA.value + nzB.value
-
-            run_blocks(1)
+            pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()
+            pa, pb, px = pin(a), pin(b), pin(x)
+            outbuf = dict(A=pin(np.zeros((m, w["k"]), dt)), B=pin(np.zeros((n, w["k"]), dt)))
+            if w["implicit"]:
+                run = lambda nit: fit_implicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=nit,
+                                               use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
+                                               copy_inputs=False, out=outbuf)
+            else:
+                outbuf.update(biasA=pin(np.zeros(m, dt)), biasB=pin(np.zeros(n, dt)))
+                run = lambda nit: fit_explicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
+                                               niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
+                                               copy_inputs=False, out=outbuf)
+            fresh_nccl_id()
+            assert L.cmfb200_set_world(rank, world, opt.nccl_id) == 0
+            assert run(1)["rc"] == 0
+            assert run(2)["rc"] == 0
             barrier()
             t0 = time.perf_counter()
-            nnz_local = run_blocks(K)
+            out = run(K)
             barrier()
             t_e2e = time.perf_counter() - t0
+            assert out["rc"] == 0
+            L.cmfb200_set_world(0, 1, None)
             tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_e2e = float(tt.item())
             wd = dt.itemsize
-            ld = ((w["k"] * wd + 127) // 128) * 128
-            h2d = nnz_local * (4 + wd) + (m + n + 2) * 8 + (m + n) * (ld + wd)
-            d2h = (m + n) * (ld + wd)
+            h2d = nnz * (8 + wd) + (m + n) * w["k"] * wd
+            d2h = (m + n) * (w["k"] + 1) * wd
             e2e = dict(value=(m + n) * K / t_e2e, unit="rows/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K,
                        seconds=t_e2e, iterations=K,
-                       what="cmfb200_als_create + set_factors + iterate + get_factors on host buffers, every rank, max over ranks "
-                            "(h2d / d2h bytes are rank 0's)")
+                       what="one fit_collective_%s_als call per rank after cmfb200_set_world, pinned host buffers in / out, max "
+                            "over ranks (h2d / d2h bytes are per rank)" % ("implicit" if w["implicit"] else "explicit"))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

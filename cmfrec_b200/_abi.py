@@ -113,7 +113,7 @@ REFERENCE_ENTRY_POINTS = ("fit_collective_explicit_als", "fit_collective_implici
 PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
     "cmfb200_real_name", "cmfb200_device_count", "cmfb200_random_init", "cmfb200_coo_to_csr_and_csc",
     "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_partition_rows", "cmfb200_nccl_unique_id", "cmfb200_als_create",
-    "cmfb200_gram", "cmfb200_trim_pool", "cmfb200_debug_poison_smem", "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
+    "cmfb200_gram", "cmfb200_set_world", "cmfb200_trim_pool", "cmfb200_debug_poison_smem", "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
     "cmfb200_als_iterate", "cmfb200_als_timed_iterate", "cmfb200_als_set_profile",
     "cmfb200_als_read_profile", "cmfb200_als_attach_collective", "cmfb200_als_get_collective", "cmfb200_als_sync", "cmfb200_als_launch_count", "cmfb200_als_local_counts",
 )
@@ -163,6 +163,8 @@ def bind_product(lib, dtype):
     lib.cmfb200_gram.argtypes = [P, c_int, c_int, P, c_int, C.POINTER(C.c_float)]
     lib.cmfb200_trim_pool.restype = None
     lib.cmfb200_trim_pool.argtypes = []
+    lib.cmfb200_set_world.restype = C.c_int
+    lib.cmfb200_set_world.argtypes = [C.c_int, C.c_int, C.c_void_p]
     lib.cmfb200_debug_poison_smem.restype = C.c_int
     lib.cmfb200_debug_poison_smem.argtypes = [C.c_uint]
     lib.cmfb200_als_destroy.argtypes = [P]

@@ -17,6 +17,12 @@ static int env_or(const char *name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
+WorldSetting &world_setting()
+{
+    static WorldSetting w;
+    return w;
+}
+
 bool devbuf_pool_enabled()
 {
     static const bool on = [] {
@@ -194,6 +200,14 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     }
     build_renumbering(csr_p, cfg.m, cfg.world, renA);
     build_renumbering(csc_p, cfg.n, cfg.world, renB);
+    if (cfg.world > 1) {
+        // the factor uploads / downloads renumber rows on the device
+        if (!renA.d_to_dev.alloc(cfg.m) || !renB.d_to_dev.alloc(cfg.n)) return 1;
+        if (cudaMemcpyAsync(renA.d_to_dev.p, renA.to_dev.data(), (size_t)cfg.m * sizeof(int_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaMemcpyAsync(renB.d_to_dev.p, renB.to_dev.data(), (size_t)cfg.n * sizeof(int_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess)
+            return 1;
+    }
     int rc = build_side(csr_p, csr_i, csr_v, renA, renB, cfg.rank, stream, byA);
     if (rc) return rc;
     rc = build_side(csc_p, csc_i, csc_v, renB, renA, cfg.rank, stream, byB);
@@ -214,6 +228,21 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
+// bucket boundaries of a side from its (descending) degree list
+static void plan_buckets(DeviceSide &side)
+{
+    const std::vector<int_t> &deg = side.deg_sorted;
+    const int_t rows = (int_t)deg.size();
+    auto count_ge = [&](size_t thr, int_t limit) {
+        int_t c = 0;
+        while (c < limit && (size_t)deg[c] >= thr) c++;
+        return c;
+    };
+    side.n_order = rows;
+    side.n_long = count_ge((size_t)long_row_threshold(), rows);
+    side.n_huge = count_ge((size_t)env_or("CMFB200_HUGE_ROW", 8192), side.n_long);
+}
+
 // processing order / bucket boundaries of a side whose ptr array is already on the device (single GPU, identity numbering)
 static int plan_side_from_device(DeviceSide &side, int_t rows, cudaStream_t stream)
 {
@@ -221,21 +250,13 @@ static int plan_side_from_device(DeviceSide &side, int_t rows, cudaStream_t stre
     side.block = rows;
     side.row_begin = 0;
     side.row_end = rows;
-    side.n_order = rows;
     if (!side.order.alloc(std::max<size_t>((size_t)rows, 1))) return 1;
     // the degree sort runs on the device (stable radix sort: ties keep increasing row order, like std::stable_sort);
     // only the sorted counts come back, for the bucket boundaries
     size_t total = 0;
     if (int rc = device_degree_order(side.ptr.p, rows, side.order.p, side.deg_sorted, &total, stream)) return rc;
     side.nnz_local = total;
-    const std::vector<int_t> &deg = side.deg_sorted;
-    auto count_ge = [&](size_t thr, int_t limit) {
-        int_t c = 0;
-        while (c < limit && (size_t)deg[c] >= thr) c++;
-        return c;
-    };
-    side.n_long = count_ge((size_t)long_row_threshold(), rows);
-    side.n_huge = count_ge((size_t)env_or("CMFB200_HUGE_ROW", 8192), side.n_long);
+    plan_buckets(side);
     return 0;
 }
 
@@ -244,153 +265,229 @@ template <typename T> __global__ void scale_kernel(T *x, size_t n, T s)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = x[i] * s;
 }
+__global__ void iota_rows_kernel(int_t *x, int_t n, int_t first)
+{
+    const int_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = first + i;
+}
+
+// one side of the multi-GPU dealing: full orientation -> this rank's block (see setup_from_coo)
+static int deal_side(DeviceSide &full, int_t rows, int rank, int world, Renumbering &ren, cudaStream_t stream,
+                     DevBuf<int_t> &order_full, std::vector<int_t> &deg_full)
+{
+    ren.block = (rows + world - 1) / world;
+    ren.rows_padded = ren.block * world;
+    if (!order_full.alloc(std::max<size_t>((size_t)rows, 1)) || !ren.d_to_dev.alloc(std::max<size_t>((size_t)rows, 1)) ||
+        !ren.d_to_old.alloc((size_t)ren.rows_padded))
+        return 1;
+    size_t total = 0;
+    if (int rc = device_degree_order(full.ptr.p, rows, order_full.p, deg_full, &total, stream)) return rc;
+    (void)rank;
+    return device_deal_rows(order_full.p, rows, world, ren.block, ren.d_to_dev.p, ren.d_to_old.p, stream);
+}
 
 int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
-                             real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later)
+                             real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later, const void *nccl_id,
+                             const BiasInit *bias, bool coo_on_device)
 {
     cfg = c;
     stream = s;
     use_resident = env_or("CMFB200_RESIDENT", 1) != 0;
     use_nm_cg = env_or("CMFB200_NMCG", 0) != 0;
-    if (cfg.world != 1) return 2;
+    if (cfg.world < 1) cfg.world = 1;
     if (cfg.kk < 1 || cfg.kk > max_supported_k()) return 2;
     if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
     cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
-    build_renumbering(nullptr, cfg.m, 1, renA);
-    build_renumbering(nullptr, cfg.n, 1, renB);
+    if (cfg.world > 1) {
+        if (!nccl_id) return 2;
+        link = new NcclLink();
+        if (link->init(nccl_id, cfg.rank, cfg.world) != 0) return 1;
+    }
+    // ---- the triplets on the device, centred / scaled
     DevBuf<int_t> dA, dB;
     DevBuf<real_t> dX;
+    const int_t *pA = ixA, *pB = ixB;
+    real_t *pX = const_cast<real_t *>(X);
     const size_t cap = std::max<size_t>(nnz, 1);
-    if (!dA.alloc(cap) || !dB.alloc(cap) || !dX.alloc(cap)) return 1;
-    if (nnz) {
-        cudaMemcpyAsync(dA.p, ixA, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(dB.p, ixB, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(dX.p, X, nnz * sizeof(real_t), cudaMemcpyHostToDevice, stream);
-        if (mu_later) mu = (*mu_later)();   // computed on a host thread while the copies above were in flight
-        if (mu != 0 && device_subtract(dX.p, nnz, mu, stream)) return 1;
-        if (scale != 1) scale_kernel<real_t><<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(dX.p, nnz, scale);
+    if (!coo_on_device) {
+        if (!dA.alloc(cap) || !dB.alloc(cap) || !dX.alloc(cap)) return 1;
+        if (nnz) {
+            if (cudaMemcpyAsync(dA.p, ixA, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+                cudaMemcpyAsync(dB.p, ixB, nnz * sizeof(int_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+                cudaMemcpyAsync(dX.p, X, nnz * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+                return 1;
+        }
+        pA = dA.p; pB = dB.p; pX = dX.p;
     }
+    if (nnz) {
+        if (mu_later) mu = (*mu_later)();   // computed on a host thread while the copies above were in flight
+        if (mu != 0 && device_subtract(pX, nnz, mu, stream)) return 1;
+        if (scale != 1) scale_kernel<real_t><<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(pX, nnz, scale);
+    }
+    // ---- both orientations in full (caller numbering)
     if (!byA.ptr.alloc((size_t)cfg.m + 1) || !byA.idx.alloc(cap) || !byA.val.alloc(cap) || !byB.ptr.alloc((size_t)cfg.n + 1) ||
         !byB.idx.alloc(cap) || !byB.val.alloc(cap))
         return 1;
-    int rc = device_compress(dA.p, dB.p, dX.p, nnz, cfg.m, byA.ptr.p, byA.idx.p, byA.val.p, stream);
+    int rc = device_compress(pA, pB, pX, nnz, cfg.m, byA.ptr.p, byA.idx.p, byA.val.p, stream);
     if (rc) return rc;
-    rc = device_compress(dB.p, dA.p, dX.p, nnz, cfg.n, byB.ptr.p, byB.idx.p, byB.val.p, stream);
+    rc = device_compress(pB, pA, pX, nnz, cfg.n, byB.ptr.p, byB.idx.p, byB.val.p, stream);
     if (rc) return rc;
     launches += 12;
-    if ((rc = plan_side_from_device(byA, cfg.m, stream))) return rc;
-    if ((rc = plan_side_from_device(byB, cfg.n, stream))) return rc;
+    dA.release(); dB.release(); dX.release();
+    // ---- starting biases from the full matrices (caller numbering)
+    DevBuf<real_t> bias_fullA, bias_fullB;
+    if (!bias_fullA.alloc((size_t)cfg.m) || !bias_fullB.alloc((size_t)cfg.n)) return 1;
+    if (cudaMemsetAsync(bias_fullA.p, 0, (size_t)cfg.m * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(bias_fullB.p, 0, (size_t)cfg.n * sizeof(real_t), stream) != cudaSuccess)
+        return 1;
+    if (bias && bias->which) {
+        if (bias->which == 3) {
+            rc = device_init_biases_twosided(cfg.m, cfg.n, byA.ptr.p, byA.idx.p, byA.val.p, byB.ptr.p, byB.idx.p, byB.val.p,
+                                             bias->lam_user, bias->lam_item, bias->scale_lam, bias_fullA.p, bias_fullB.p, stream);
+            launches += 10;
+        } else if (bias->which == 1) {
+            rc = device_init_biases_onesided(cfg.m, byA.ptr.p, byA.val.p, bias->lam_user, bias->scale_lam, bias_fullA.p, stream);
+            launches += 1;
+        } else if (bias->which == 2) {
+            rc = device_init_biases_onesided(cfg.n, byB.ptr.p, byB.val.p, bias->lam_item, bias->scale_lam, bias_fullB.p, stream);
+            launches += 1;
+        }
+        if (rc) return rc;
+    }
     ldA = cmf_ld_for(cfg.kk);
     ldB = cmf_ld_for(cfg.kk);
+    if (cfg.world == 1) {
+        build_renumbering(nullptr, cfg.m, 1, renA);
+        build_renumbering(nullptr, cfg.n, 1, renB);
+        if ((rc = plan_side_from_device(byA, cfg.m, stream))) return rc;
+        if ((rc = plan_side_from_device(byB, cfg.n, stream))) return rc;
+    } else {
+        // ---- deal the rows to the ranks and keep this rank's blocks
+        DeviceSide fullA, fullB;
+        fullA.ptr.swap(byA.ptr); fullA.idx.swap(byA.idx); fullA.val.swap(byA.val);
+        fullB.ptr.swap(byB.ptr); fullB.idx.swap(byB.idx); fullB.val.swap(byB.val);
+        DevBuf<int_t> orderA, orderB;
+        std::vector<int_t> degA, degB;
+        if ((rc = deal_side(fullA, cfg.m, cfg.rank, cfg.world, renA, stream, orderA, degA))) return rc;
+        if ((rc = deal_side(fullB, cfg.n, cfg.rank, cfg.world, renB, stream, orderB, degB))) return rc;
+        auto extract = [&](DeviceSide &full, const std::vector<int_t> &deg, int_t rows, Renumbering &ren, Renumbering &other,
+                           DeviceSide &side) -> int {
+            side.rows_padded = ren.rows_padded;
+            side.block = ren.block;
+            side.row_begin = cfg.rank * ren.block;
+            side.row_end = side.row_begin + ren.block;
+            // sorted positions rank, rank + world, ... are this rank's rows, already in decreasing-degree order
+            const int_t n_local = rows > cfg.rank ? (rows - cfg.rank + cfg.world - 1) / cfg.world : 0;
+            side.deg_sorted.resize((size_t)n_local);
+            for (int_t i = 0; i < n_local; i++) side.deg_sorted[i] = deg[(size_t)cfg.rank + (size_t)i * cfg.world];
+            plan_buckets(side);
+            if (!side.order.alloc(std::max<size_t>((size_t)n_local, 1))) return 1;
+            if (n_local > 0) iota_rows_kernel<<<(n_local + 255) / 256, 256, 0, stream>>>(side.order.p, n_local, side.row_begin);
+            return device_extract_block(full.ptr.p, full.idx.p, full.val.p, ren.d_to_old.p, other.d_to_dev.p, side.row_begin,
+                                        side.row_end, n_local, ren.rows_padded, side.ptr, side.idx, side.val, &side.nnz_local, stream);
+        };
+        if ((rc = extract(fullA, degA, cfg.m, renA, renB, byA))) return rc;
+        if ((rc = extract(fullB, degB, cfg.n, renB, renA, byB))) return rc;
+        launches += 10;
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;   // the full matrices are released on leaving this scope
+    }
     if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB) ||
         !biasA.alloc(renA.rows_padded) || !biasB.alloc(renB.rows_padded))
         return 1;
-    cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream);
-    cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream);
-    cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream);
-    cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream);
+    if (cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream) != cudaSuccess)
+        return 1;
+    if ((rc = device_scatter_rows(bias_fullA.p, 1, cfg.m, 1, renA.d_to_dev.p, biasA.p, 1, stream))) return rc;
+    if ((rc = device_scatter_rows(bias_fullB.p, 1, cfg.n, 1, renB.d_to_dev.p, biasB.p, 1, stream))) return rc;
     if (cfg.implicit) {
         if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
         if (device_all_positive(byA.val.p, byA.nnz_local, &values_positive, stream)) return 1;
+        if (link) {
+            // every rank must take the same kernel: positive everywhere or nowhere
+            int flag = values_positive ? 0 : 1;
+            DevBuf<real_t> f;
+            if (!f.alloc(1)) return 1;
+            const real_t hv = (real_t)flag;
+            cudaMemcpyAsync(f.p, &hv, sizeof(real_t), cudaMemcpyHostToDevice, stream);
+            if (link->all_reduce_sum(f.p, 1, sizeof(real_t) == 8, stream)) return 1;
+            real_t out = 0;
+            cudaMemcpyAsync(&out, f.p, sizeof(real_t), cudaMemcpyDeviceToHost, stream);
+            if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+            values_positive = out == real_t(0);
+        }
     }
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
-int AlsState::init_biases_on_device(int which, real_t lam_user, real_t lam_item, bool scale_lam)
+// rows of a host matrix [rows x kk] (row stride ldh, caller numbering) -> device rows (stride ld, device numbering)
+static int upload_rows(const real_t *h, int ldh, int_t rows, int kk, const Renumbering &ren, real_t *dst, int ld, cudaStream_t stream)
 {
-    int rc = 0;
-    if (which == 3) {
-        rc = device_init_biases_twosided(cfg.m, cfg.n, byA.ptr.p, byA.idx.p, byA.val.p, byB.ptr.p, byB.idx.p, byB.val.p, lam_user,
-                                         lam_item, scale_lam, biasA.p, biasB.p, stream);
-        launches += 10;
-    } else if (which == 1) {
-        rc = device_init_biases_onesided(cfg.m, byA.ptr.p, byA.val.p, lam_user, scale_lam, biasA.p, stream);
-        launches += 1;
-    } else if (which == 2) {
-        rc = device_init_biases_onesided(cfg.n, byB.ptr.p, byB.val.p, lam_item, scale_lam, biasB.p, stream);
-        launches += 1;
-    }
-    if (rc) return rc;
-    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+    const size_t w = (size_t)kk * sizeof(real_t);
+    if (!ren.d_to_dev.p)
+        return cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(real_t), h, (size_t)ldh * sizeof(real_t), w, rows, cudaMemcpyHostToDevice,
+                                 stream) == cudaSuccess ? 0 : 1;
+    DevBuf<real_t> tmp;
+    if (!tmp.alloc((size_t)rows * kk)) return 1;
+    if (cudaMemcpy2DAsync(tmp.p, w, h, (size_t)ldh * sizeof(real_t), w, rows, cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
+    if (device_scatter_rows(tmp.p, kk, rows, kk, ren.d_to_dev.p, dst, ld, stream)) return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;   // tmp is released on return
 }
-
-static void pack_factor(const real_t *h, int ldh, const real_t *hbias, int_t rows, int kk, const Renumbering &ren, int ld,
-                        std::vector<real_t> &out, std::vector<real_t> &bias_out)
+static int download_rows(const real_t *src, int ld, int_t rows, int kk, const Renumbering &ren, real_t *h, int ldh, cudaStream_t stream)
 {
-    out.assign((size_t)ren.rows_padded * ld, real_t(0));
-    bias_out.assign((size_t)ren.rows_padded, real_t(0));
-#pragma omp parallel for schedule(static)
-    for (long long r = 0; r < (long long)rows; r++) {
-        real_t *dst = out.data() + (size_t)ren.to_dev[r] * ld;
-        std::memcpy(dst, h + (size_t)r * ldh, (size_t)kk * sizeof(real_t));
-        if (hbias) bias_out[ren.to_dev[r]] = hbias[r];
-    }
+    const size_t w = (size_t)kk * sizeof(real_t);
+    if (!ren.d_to_dev.p)
+        return cudaMemcpy2DAsync(h, (size_t)ldh * sizeof(real_t), src, (size_t)ld * sizeof(real_t), w, rows, cudaMemcpyDeviceToHost,
+                                 stream) == cudaSuccess ? 0 : 1;
+    DevBuf<real_t> tmp;
+    if (!tmp.alloc((size_t)rows * kk)) return 1;
+    if (device_gather_rows_back(src, ld, rows, kk, ren.d_to_dev.p, tmp.p, kk, stream)) return 1;
+    if (cudaMemcpy2DAsync(h, (size_t)ldh * sizeof(real_t), tmp.p, w, w, rows, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
 int AlsState::upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb,
                              const real_t *hbiasB)
 {
-    std::vector<real_t> tmp, tb;
-    pack_factor(hA, lda, hbiasA, cfg.m, cfg.kk, renA, ldA, tmp, tb);
-    if (cudaMemcpyAsync(A.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+    // padding columns / rows and absent biases read as zero
+    if (cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream) != cudaSuccess)
         return 1;
-    cudaMemcpyAsync(biasA.p, tb.data(), tb.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream);
-    cudaStreamSynchronize(stream);
-    pack_factor(hB, ldb, hbiasB, cfg.n, cfg.kk, renB, ldB, tmp, tb);
-    if (cudaMemcpyAsync(B.p, tmp.data(), tmp.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess)
-        return 1;
-    cudaMemcpyAsync(biasB.p, tb.data(), tb.size() * sizeof(real_t), cudaMemcpyHostToDevice, stream);
+    if (hA && upload_rows(hA, lda, cfg.m, cfg.kk, renA, A.p, ldA, stream)) return 1;
+    if (hB && upload_rows(hB, ldb, cfg.n, cfg.kk, renB, B.p, ldB, stream)) return 1;
+    if (hbiasA && upload_rows(hbiasA, 1, cfg.m, 1, renA, biasA.p, 1, stream)) return 1;
+    if (hbiasB && upload_rows(hbiasB, 1, cfg.n, 1, renB, biasB.p, 1, stream)) return 1;
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
-// biases of one side from a host array (identity numbering): which = 1 users, 2 items
+// biases of one side from a host array (caller numbering): which = 1 users, 2 items
 int AlsState::upload_bias(int which, const real_t *hbias)
 {
-    if (cfg.world != 1 || !hbias) return 2;
-    real_t *dst = which == 1 ? biasA.p : biasB.p;
-    const int_t rows = which == 1 ? cfg.m : cfg.n;
-    if (cudaMemcpyAsync(dst, hbias, (size_t)rows * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
+    if (!hbias) return 2;
+    const int rc = which == 1 ? upload_rows(hbias, 1, cfg.m, 1, renA, biasA.p, 1, stream) : upload_rows(hbias, 1, cfg.n, 1, renB, biasB.p, 1, stream);
+    if (rc) return rc;
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
-// factor coordinates only (bias slots and padding on the device are left untouched); identity numbering
+// factor coordinates only (bias slots and padding on the device are left untouched)
 int AlsState::upload_coordinates(const real_t *hA, const real_t *hB)
 {
-    if (cfg.world != 1) return 2;
-    const size_t w = (size_t)cfg.kk * sizeof(real_t);
-    if (hA && cudaMemcpy2DAsync(A.p, (size_t)ldA * sizeof(real_t), hA, w, w, cfg.m, cudaMemcpyHostToDevice, stream) != cudaSuccess)
-        return 1;
-    if (hB && cudaMemcpy2DAsync(B.p, (size_t)ldB * sizeof(real_t), hB, w, w, cfg.n, cudaMemcpyHostToDevice, stream) != cudaSuccess)
-        return 1;
+    if (hA && upload_rows(hA, cfg.kk, cfg.m, cfg.kk, renA, A.p, ldA, stream)) return 1;
+    if (hB && upload_rows(hB, cfg.kk, cfg.n, cfg.kk, renB, B.p, ldB, stream)) return 1;
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
-}
-
-static void unpack_factor(const std::vector<real_t> &in, const std::vector<real_t> &bias_in, int ld, const Renumbering &ren,
-                          int_t rows, int kk, real_t *h, int ldh, real_t *hbias)
-{
-#pragma omp parallel for schedule(static)
-    for (long long r = 0; r < (long long)rows; r++) {
-        const real_t *src = in.data() + (size_t)ren.to_dev[r] * ld;
-        if (h) std::memcpy(h + (size_t)r * ldh, src, (size_t)kk * sizeof(real_t));
-        if (hbias) hbias[r] = bias_in[ren.to_dev[r]];
-    }
 }
 
 int AlsState::download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB)
 {
-    std::vector<real_t> tmp(A.n), tb(biasA.n);
-    if (cudaMemcpyAsync(tmp.data(), A.p, A.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
-    cudaMemcpyAsync(tb.data(), biasA.p, biasA.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream);
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
-    unpack_factor(tmp, tb, ldA, renA, cfg.m, cfg.kk, hA, lda, hbiasA);
-    tmp.resize(B.n);
-    tb.resize(biasB.n);
-    if (cudaMemcpyAsync(tmp.data(), B.p, B.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
-    cudaMemcpyAsync(tb.data(), biasB.p, biasB.n * sizeof(real_t), cudaMemcpyDeviceToHost, stream);
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
-    unpack_factor(tmp, tb, ldB, renB, cfg.n, cfg.kk, hB, ldb, hbiasB);
-    return 0;
+    if (hA && download_rows(A.p, ldA, cfg.m, cfg.kk, renA, hA, lda, stream)) return 1;
+    if (hB && download_rows(B.p, ldB, cfg.n, cfg.kk, renB, hB, ldb, stream)) return 1;
+    if (hbiasA && download_rows(biasA.p, 1, cfg.m, 1, renA, hbiasA, 1, stream)) return 1;
+    if (hbiasB && download_rows(biasB.p, 1, cfg.n, 1, renB, hbiasB, 1, stream)) return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
 int AlsState::half_sweep(int which, int iter, int solver)
@@ -415,10 +512,18 @@ int AlsState::half_sweep(int which, int iter, int solver)
     const bool both = cfg.user_bias && cfg.item_bias;
     if (cfg.implicit) {
         p.solve_bias = p.center_opp = p.bias_start_one = false;
-        const int_t opp_rows = solveA ? renB.rows_padded : renA.rows_padded;
-        int rc = launch_gram(p.G, p.ldG, opp_rows, cfg.kk, gram.p, gram_ws.p, stream);
+        // Gram of the opposing factor: every rank multiplies its own block of rows, the k x k partials are all-reduced
+        // (the sum order over the ranks is NCCL's: multi-GPU implicit fits differ from the one-GPU fit by that noise)
+        const Renumbering &oren = solveA ? renB : renA;
+        const int_t opp_rows = link ? oren.block : oren.rows_padded;
+        const real_t *opp = p.G + (link ? (size_t)cfg.rank * oren.block * p.ldG : 0);
+        int rc = launch_gram(opp, p.ldG, opp_rows, cfg.kk, gram.p, gram_ws.p, stream);
         launches += 2;
         if (rc) return rc;
+        if (link) {
+            if ((rc = link->all_reduce_sum(gram.p, (size_t)cfg.kk * cfg.kk, sizeof(real_t) == 8, stream))) return rc;
+            launches += 1;
+        }
         p.gram = gram.p;
         p.values_positive = values_positive;
     } else {

@@ -42,6 +42,12 @@ template <typename T> struct DevBuf {
         p = nullptr;
         n = 0;
     }
+    void swap(DevBuf &o)
+    {
+        std::swap(p, o.p);
+        std::swap(n, o.n);
+        std::swap(pooled, o.pooled);
+    }
     bool alloc(size_t count)
     {
         release();
@@ -78,9 +84,18 @@ struct DeviceSide {
 };
 
 struct Renumbering {              // old (caller) row id <-> device row id
-    std::vector<int_t> to_dev;    // [rows]
+    std::vector<int_t> to_dev;    // [rows]          host copies: only filled by the host-side dealing of setup()
     std::vector<int_t> to_old;    // [rows_padded], -1 for padding rows
+    DevBuf<int_t> d_to_dev;       // [rows] on the device; null = identity numbering (one rank)
+    DevBuf<int_t> d_to_old;       // [rows_padded]
     int_t block = 0, rows_padded = 0;
+};
+
+// starting biases computed on the device while X is ingested (AlsState::setup_from_coo)
+struct BiasInit {
+    int which = 0;                // 0 none, 3 both sides (two-sided sweeps), 1 users only, 2 items only
+    real_t lam_user = 0, lam_item = 0;
+    bool scale_lam = false;
 };
 
 struct AlsConfig {
@@ -99,6 +114,13 @@ void build_renumbering(const size_t *ptr, int_t rows, int world, Renumbering &re
 
 class NcclLink;
 class CollectiveState;
+
+// Which rank of how many the reference-named fit entry points run as (cmfb200_set_world); one process drives one GPU.
+struct WorldSetting {
+    int rank = 0, world = 1;
+    unsigned char nccl_id[128] = {0};
+};
+WorldSetting &world_setting();
 
 class AlsState {
 public:
@@ -135,11 +157,13 @@ public:
               const int_t *csc_i, const real_t *csc_v, cudaStream_t s, const void *nccl_id);
     // single-GPU ingestion straight from host COO triplets: upload, subtract `mu`, multiply by `scale`, build both
     // orientations on the device (device_prep.cu).  Values are transformed as  (x - mu) * scale  in real_t.
+    // With cfg.world > 1 (nccl_id: the communicator's unique id) every rank passes the SAME triplets: both orientations are
+    // built in full on every device, the rows are dealt to the ranks there (decreasing degree, round-robin) and only this
+    // rank's blocks are kept.  coo_on_device: ixA / ixB / X are device pointers already.  bias: starting biases computed
+    // on the device from the full matrices (before the dealing) and stored in device numbering.
     int setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
-                       real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later = nullptr);   // mu_later: the mean is still being computed on the host; asked for once the uploads are in flight
-    // starting biases computed on the device and written into the bias slots of A / B
-    // which: 3 = both sides (two-sided sweeps), 1 = users only, 2 = items only
-    int init_biases_on_device(int which, real_t lam_user, real_t lam_item, bool scale_lam);
+                       real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later = nullptr,   // mu_later: the mean is still being computed on the host; asked for once the uploads are in flight
+                       const void *nccl_id = nullptr, const BiasInit *bias = nullptr, bool coo_on_device = false);
     // factors in caller numbering: A [m x kk] (ld = lda), biasA [m] or null; same for B
     int upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb, const real_t *hbiasB);
     int upload_coordinates(const real_t *hA, const real_t *hB);   // keeps the bias slots already on the device

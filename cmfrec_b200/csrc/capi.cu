@@ -3,6 +3,7 @@
 // host_prep.cpp, popular.cpp and topn.cu.
 #include "../../include/cmfrec_b200.h"
 #include <cstdio>
+#include <cstring>
 #include "als.h"
 #include "collective.h"
 #include "fit.h"
@@ -272,6 +273,23 @@ int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats,
 }
 
 void cmfb200_trim_pool(void) { cmfb200::devbuf_trim_pool(); }
+
+// Every later fit_collective_*_als call of this process runs as rank `rank` of `world` (one process per GPU, the same
+// arguments on every rank, every rank receives the full result); world = 1 switches back.
+int cmfb200_set_world(int rank, int world, const void *nccl_id128)
+{
+    cmfb200::WorldSetting &w = cmfb200::world_setting();
+    if (world <= 1) {
+        w.rank = 0;
+        w.world = 1;
+        return 0;
+    }
+    if (rank < 0 || rank >= world || !nccl_id128) return 2;
+    w.rank = rank;
+    w.world = world;
+    std::memcpy(w.nccl_id, nccl_id128, 128);
+    return 0;
+}
 
 namespace {
 __global__ void poison_smem_kernel(unsigned pattern)

@@ -256,6 +256,131 @@ int device_degree_order(const size_t *d_ptr, int_t rows, int_t *d_order, std::ve
     return cudaStreamSynchronize(stream) == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+namespace {
+// sorted position s of a row -> device row (s % world) * block + s / world: rows are dealt round-robin in order of
+// decreasing degree (equal blocks for the all-gather, near-equal numbers of stored entries)
+__global__ void deal_kernel(const int_t *__restrict__ order, int_t rows, int world, int_t block, int_t *__restrict__ to_dev,
+                            int_t *__restrict__ to_old)
+{
+    const int_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < rows) {
+        const int_t r = order[s];
+        const int_t dev = (s % world) * block + s / world;
+        to_dev[r] = dev;
+        to_old[dev] = r;
+    }
+}
+__global__ void fill_kernel(int_t *x, size_t n, int_t v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+// number of stored entries of every device row held by this rank (0 for the rows of other ranks and for padding)
+__global__ void local_len_kernel(const size_t *__restrict__ ptr_full, const int_t *__restrict__ to_old, int_t row_begin,
+                                 int_t row_end, int_t rows_padded, unsigned long long *__restrict__ len)
+{
+    const int_t dev = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dev <= rows_padded) {
+        unsigned long long l = 0;
+        if (dev >= row_begin && dev < row_end && dev < rows_padded) {
+            const int_t old = to_old[dev];
+            if (old >= 0) l = ptr_full[old + 1] - ptr_full[old];
+        }
+        len[dev] = l;
+    }
+}
+// one warp per local row: copy its entries, column ids renumbered into the other side's device numbering
+__global__ void gather_rows_kernel(const size_t *__restrict__ ptr_full, const int_t *__restrict__ idx_full,
+                                   const real_t *__restrict__ val_full, const int_t *__restrict__ to_old,
+                                   const int_t *__restrict__ other_to_dev, int_t row_begin, int_t n_local,
+                                   const size_t *__restrict__ ptr_local, int_t *__restrict__ idx_local,
+                                   real_t *__restrict__ val_local)
+{
+    const int_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_local) return;
+    const int_t dev = row_begin + i;
+    const int_t old = to_old[dev];
+    if (old < 0) return;
+    const size_t src = ptr_full[old], cnt = ptr_full[old + 1] - src, dst = ptr_local[dev];
+    for (size_t e = lane; e < cnt; e += 32) {
+        idx_local[dst + e] = other_to_dev[idx_full[src + e]];
+        val_local[dst + e] = val_full[src + e];
+    }
+}
+// rows of a dense host-numbered matrix -> device numbering with padded stride (and back)
+__global__ void scatter_rows_kernel(const real_t *__restrict__ src, int lds, int_t rows, int kk, const int_t *__restrict__ to_dev,
+                                    real_t *__restrict__ dst, int ldd)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)rows * kk) return;
+    const int_t r = (int_t)(t / kk);
+    const int c = (int)(t - (size_t)r * kk);
+    dst[(size_t)(to_dev ? to_dev[r] : r) * ldd + c] = src[(size_t)r * lds + c];
+}
+__global__ void gather_back_kernel(const real_t *__restrict__ src, int lds, int_t rows, int kk, const int_t *__restrict__ to_dev,
+                                   real_t *__restrict__ dst, int ldd)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)rows * kk) return;
+    const int_t r = (int_t)(t / kk);
+    const int c = (int)(t - (size_t)r * kk);
+    dst[(size_t)r * ldd + c] = src[(size_t)(to_dev ? to_dev[r] : r) * lds + c];
+}
+}  // namespace
+
+// d_order: rows by decreasing degree (device_degree_order).  Fills to_dev [rows] and to_old [world * block] (-1 = padding).
+int device_deal_rows(const int_t *d_order, int_t rows, int world, int_t block, int_t *d_to_dev, int_t *d_to_old, cudaStream_t stream)
+{
+    const size_t padded = (size_t)world * block;
+    fill_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, stream>>>(d_to_old, padded, (int_t)-1);
+    if (rows > 0) deal_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(d_order, rows, world, block, d_to_dev, d_to_old);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// This rank's block of one orientation out of the full matrix: ptr_local [rows_padded + 1] (device row ids; rows of other
+// ranks are empty), idx / val of the local entries with column ids in the other side's device numbering.
+// *nnz_local receives the number of local entries (synchronises).  idx_local / val_local are allocated here.
+int device_extract_block(const size_t *ptr_full, const int_t *idx_full, const real_t *val_full, const int_t *to_old,
+                         const int_t *other_to_dev, int_t row_begin, int_t row_end, int_t n_local, int_t rows_padded,
+                         DevBuf<size_t> &ptr_local, DevBuf<int_t> &idx_local, DevBuf<real_t> &val_local, size_t *nnz_local,
+                         cudaStream_t stream)
+{
+    DevBuf<unsigned long long> len;
+    if (!len.alloc((size_t)rows_padded + 1) || !ptr_local.alloc((size_t)rows_padded + 1)) return 1;
+    local_len_kernel<<<(rows_padded + 1 + 255) / 256, 256, 0, stream>>>(ptr_full, to_old, row_begin, row_end, rows_padded, len.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, len.p, reinterpret_cast<unsigned long long *>(ptr_local.p), rows_padded + 1, stream);
+    DevBuf<unsigned char> tmp;
+    if (!tmp.alloc(tb ? tb : 1)) return 1;
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.p, reinterpret_cast<unsigned long long *>(ptr_local.p), rows_padded + 1, stream);
+    size_t total = 0;
+    if (cudaMemcpyAsync(&total, ptr_local.p + rows_padded, sizeof(size_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+        return 1;
+    *nnz_local = total;
+    if (!idx_local.alloc(total ? total : 1) || !val_local.alloc(total ? total : 1)) return 1;
+    if (n_local > 0 && total > 0) {
+        const long long threads = (long long)n_local * 32;
+        gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(ptr_full, idx_full, val_full, to_old, other_to_dev,
+                                                                                   row_begin, n_local, ptr_local.p, idx_local.p, val_local.p);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int device_scatter_rows(const real_t *src, int lds, int_t rows, int kk, const int_t *to_dev, real_t *dst, int ldd, cudaStream_t stream)
+{
+    const size_t n = (size_t)rows * kk;
+    if (n) scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, lds, rows, kk, to_dev, dst, ldd);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+int device_gather_rows_back(const real_t *src, int lds, int_t rows, int kk, const int_t *to_dev, real_t *dst, int ldd, cudaStream_t stream)
+{
+    const size_t n = (size_t)rows * kk;
+    if (n) gather_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, lds, rows, kk, to_dev, dst, ldd);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int device_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
                                 const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, real_t lam_user, real_t lam_item,
                                 bool scale_lam, real_t *d_biasA, real_t *d_biasB, cudaStream_t stream)

@@ -140,23 +140,28 @@ int fit_explicit(const ExplicitArgs &a)
     cfg.max_cg_steps = a.max_cg_steps;
     (void)lam;
 
-    // upload COO, centre, build CSR + CSC on the device (src/collective.c:7593 -> src/helpers.c:1375)
+    // upload COO, centre, build CSR + CSC on the device (src/collective.c:7593 -> src/helpers.c:1375), starting biases
+    // (src/collective.c:8164-8226) from the full matrices, then (world > 1) deal the rows to the ranks
+    const WorldSetting &ws = world_setting();
+    cfg.rank = ws.rank;
+    cfg.world = ws.world;
+    if (cfg.world > 1 && collective) return refuse("side information / implicit features on more than one GPU");
+    BiasInit bi;
+    if (has_bias) {
+        if (a.user_bias && a.item_bias) bi.which = 3;
+        else if (a.user_bias) bi.which = 1;
+        else if (use_cg) bi.which = 2;
+        bi.lam_user = lam_u[0];
+        bi.lam_item = lam_u[1];
+        bi.scale_lam = scale_lam;
+    }
     AlsState st;
-    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, a.X, nnz, real_t(0), real_t(1), nullptr, &mean_later);
+    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, a.X, nnz, real_t(0), real_t(1), nullptr, &mean_later,
+                               cfg.world > 1 ? ws.nccl_id : nullptr, &bi);
     mean_later();
     if (a.glob_mean) *a.glob_mean = glob_mean;
     if (rc) return rc == 2 ? refuse("this value of k") : rc;
-    tm.lap("global mean (host thread) + upload COO + CSR/CSC (GPU)");
-
-    // starting biases (src/collective.c:8164-8226)
-    if (has_bias) {
-        int which = 0;
-        if (a.user_bias && a.item_bias) which = 3;
-        else if (a.user_bias) which = 1;
-        else if (use_cg) which = 2;
-        if (which && (rc = st.init_biases_on_device(which, lam_u[0], lam_u[1], scale_lam))) return rc;
-    }
-    tm.lap("bias initialisation (GPU)");
+    tm.lap("mean (host thread) + upload COO + CSR/CSC + biases (GPU)");
 
     rng.join();
     tm.lap("factor initialisation (host)");
@@ -273,8 +278,12 @@ int fit_implicit(const ImplicitArgs &a)
     cfg.lam_A = lamA; cfg.lam_B = lamB;
     cfg.max_cg_steps = a.max_cg_steps;
 
+    const WorldSetting &ws = world_setting();
+    cfg.rank = ws.rank;
+    cfg.world = ws.world;
     AlsState st;
-    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, Xsrc, nnz, real_t(0), a.alpha, nullptr);
+    int rc = st.setup_from_coo(cfg, a.ixA, a.ixB, Xsrc, nnz, real_t(0), a.alpha, nullptr, nullptr,
+                               cfg.world > 1 ? ws.nccl_id : nullptr);
     if (rc) return rc == 2 ? refuse("this value of k") : rc;
     tm.lap("upload COO + CSR/CSC (GPU)");
     rng.join();

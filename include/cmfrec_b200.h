@@ -201,6 +201,12 @@ typedef struct cmfb200_als_options {
 } cmfb200_als_options;
 
 int cmfb200_nccl_unique_id(void *out128);
+/* Multi-GPU behind the reference-named entry points (which carry no communicator argument): after this call every
+ * fit_collective_explicit_als / fit_collective_implicit_als of the process runs as rank `rank` of `world` ranks, one process
+ * per GPU.  Every rank passes the same arguments and receives the full factors; X is ingested on every device, the rows
+ * are dealt to the ranks there.  nccl_id128: the 128 bytes of cmfb200_nccl_unique_id from rank 0, identical on all ranks.
+ * world <= 1 returns to single-GPU operation. */
+int cmfb200_set_world(int rank, int world, const void *nccl_id128);
 
 /* How rows are dealt to ranks: row r of the caller's numbering lives at device row to_device_row[r]; rank q owns
  * device rows [q*block, (q+1)*block).  Rows are dealt round-robin in order of decreasing number of stored entries
