@@ -3,6 +3,7 @@
 #include "nccl_link.h"
 #include "device_prep.h"
 #include "collective.h"
+#include "dense_small.h"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,12 @@ WorldSetting &world_setting()
 {
     static WorldSetting w;
     return w;
+}
+
+volatile int &stop_flag()
+{
+    static volatile int flag = 0;
+    return flag;
 }
 
 bool devbuf_pool_enabled()
@@ -526,6 +533,15 @@ int AlsState::half_sweep(int which, int iter, int solver)
         }
         p.gram = gram.p;
         p.values_positive = values_positive;
+        // implicit feedback WITH side information (collective.cu): the constant matrix becomes G^T G + w C^T C, every row
+        // gets the vector w C^T u_i and is solved whether or not it has entries (src/collective.c:2905-3269, 1849-2132)
+        if (extraQ[which ? 1 : 0]) {
+            if ((rc = launch_axpby(cfg.kk * cfg.kk, real_t(1), gram.p, real_t(1), extraQ[which ? 1 : 0], gram.p, stream))) return rc;
+            launches += 1;
+        }
+        p.qvec = extraq[which ? 1 : 0];
+        p.ldq = extra_ldq[which ? 1 : 0];
+        p.solve_all_rows = extra_all_rows[which ? 1 : 0];
     } else {
         p.solve_bias = solveA ? cfg.user_bias : cfg.item_bias;
         p.center_opp = solveA ? cfg.item_bias : cfg.user_bias;
@@ -626,19 +642,36 @@ int AlsState::exchange(int which)
 
 int AlsState::iterate(int first_iter, int n_iters, int niter_total, bool use_cg, bool finalize_chol)
 {
+    // returns 3 when a stop was requested (SIGINT): polled before every half-sweep like the reference does
+    // (src/collective.c:8343, 8612, 8800); the state then holds the factors of the last completed half-sweep
+    auto say = [&](const char *what) {
+        if (verbose) {
+            std::printf("%s", what);
+            std::fflush(stdout);
+        }
+    };
     for (int it = first_iter; it < first_iter + n_iters; it++) {
         // the reference switches the last iteration to the exact solver (src/collective.c:8336-8340)
         const bool cg_now = use_cg && !(finalize_chol && it == niter_total - 1);
         const int solver = cg_now ? 0 : 1;
         if (coll) {
             if (int rcc = coll->iteration(it, solver)) return rcc;
-            continue;
+        } else {
+            if (stop_flag()) return 3;
+            say("Updating B ...");
+            int rc = half_sweep(0, it, solver);
+            if (rc) return rc;
+            if ((rc = exchange(0))) return rc;
+            if (verbose && cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+            say(" done\n");
+            if (stop_flag()) return 3;
+            say("Updating A ...");
+            if ((rc = half_sweep(1, it, solver))) return rc;
+            if ((rc = exchange(1))) return rc;
+            if (verbose && cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+            say(" done\n");
         }
-        int rc = half_sweep(0, it, solver);
-        if (rc) return rc;
-        if ((rc = exchange(0))) return rc;
-        if ((rc = half_sweep(1, it, solver))) return rc;
-        if ((rc = exchange(1))) return rc;
+        if (verbose) std::printf("\tCompleted ALS iteration %2d\n\n", it + 1);
     }
     return 0;
 }

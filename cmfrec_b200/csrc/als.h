@@ -121,6 +121,8 @@ struct WorldSetting {
     unsigned char nccl_id[128] = {0};
 };
 WorldSetting &world_setting();
+// set asynchronously (SIGINT handler installed by the fit entry points); polled between half-sweeps
+volatile int &stop_flag();
 
 class AlsState {
 public:
@@ -143,6 +145,7 @@ public:
     int extra_ldq[2] = {0, 0};
     bool extra_all_rows[2] = {false, false};
     bool values_positive = false;   // implicit model: every stored value is > 0 (checked once when the state is set up)
+    bool verbose = false;         // progress lines on stdout like the reference's ("Updating B ... done")
     bool use_nm_cg = false;       // CMFB200_NMCG=1: run the explicit model's CG on the tensor-core-built normal matrix (sweep_nm.cu)
     bool use_resident = true;     // CMFB200_RESIDENT=0 selects the direct-gather CG kernel (read when the state is set up)
     long long launches = 0;       // kernels launched so far (for bench.py's gpu_launches)

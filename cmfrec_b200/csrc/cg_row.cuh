@@ -254,7 +254,7 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
         if (hb) ab = p.bias_start_one ? T(1) : p.Fbias[row];
 
         T lam = p.lam, lam_last = p.lam_last;
-        if (!IMPLICIT && p.scale_lam && nnz > 0) {   // rows without entries (collective model only) keep lam as is
+        if (!IMPLICIT && p.scale_lam && nnz > 0) {   // rows without entries (models with side information only) keep lam as is
             lam *= (T)nnz;
             if (!p.scale_bias_const) lam_last *= (T)nnz;
         }
@@ -270,7 +270,7 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
         for (int j = 0; j < C; j++) {
             const int c = Lay::col(l, j);
             r[j] = (c < kk) ? fma(-lam, a[j], acc[j]) : T(0);
-            if constexpr (MODEL == kModelCollective) {
+            if constexpr (MODEL != kModelExplicit) {   // side information: explicit + collective model, or implicit with U / I
                 if (p.qvec && c < kk) r[j] += p.qvec[(size_t)row * (size_t)p.ldq + c];
             }
         }

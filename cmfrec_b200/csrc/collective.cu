@@ -111,23 +111,54 @@ int CollectiveState::build_extras(int which, const DeviceSide &side, int_t rows,
 
 int CollectiveState::iteration(int it, int solver)
 {
-    const int k = st->cfg.kk;
     const int_t m = st->cfg.m, n = st->cfg.n;
-    (void)k;
     int rc;
+    auto say = [&](const char *what) {
+        if (st->verbose) {
+            std::printf("%s", what);
+            std::fflush(stdout);
+        }
+    };
+    auto done = [&]() -> int {
+        if (st->verbose && cudaStreamSynchronize(st->stream) != cudaSuccess) return 1;
+        say(" done\n");
+        return 0;
+    };
     // C and D from the current A and B
-    if (cc.p > 0 && (rc = update_side_factor(st->A.p, st->ldA, m, Uc.p, cc.p, cc.lam_C, C.p))) return rc;
-    if (cc.q > 0 && (rc = update_side_factor(st->B.p, st->ldB, n, Ic.p, cc.q, cc.lam_D, D.p))) return rc;
+    if (cc.p > 0) {
+        if (stop_flag()) return 3;
+        say("Updating C ...");
+        if ((rc = update_side_factor(st->A.p, st->ldA, m, Uc.p, cc.p, cc.lam_C, C.p))) return rc;
+        if ((rc = done())) return rc;
+    }
+    if (cc.q > 0) {
+        if (stop_flag()) return 3;
+        say("Updating D ...");
+        if ((rc = update_side_factor(st->B.p, st->ldB, n, Ic.p, cc.q, cc.lam_D, D.p))) return rc;
+        if ((rc = done())) return rc;
+    }
     // Bi from A, Ai from B (both before B and A are touched)
     if (cc.implicit_features) {
+        if (stop_flag()) return 3;
+        say("Updating Bi...");
         if ((rc = update_implicit_factor(st->byB, st->A.p, st->ldA, m, cc.lam_Bi, Bi.p))) return rc;
+        if ((rc = done())) return rc;
+        if (stop_flag()) return 3;
+        say("Updating Ai...");
         if ((rc = update_implicit_factor(st->byA, st->B.p, st->ldB, n, cc.lam_Ai, Ai.p))) return rc;
+        if ((rc = done())) return rc;
     }
     // B given A (extras use D and Ai), then A given the new B (extras use C and Bi)
+    if (stop_flag()) return 3;
+    say("Updating B ...");
     if ((rc = build_extras(0, st->byB, n, Ic.p, cc.q, D.p, cc.w_item, Ai.p, m))) return rc;
     if ((rc = st->half_sweep(0, it, solver))) return rc;
+    if ((rc = done())) return rc;
+    if (stop_flag()) return 3;
+    say("Updating A ...");
     if ((rc = build_extras(1, st->byA, m, Uc.p, cc.p, C.p, cc.w_user, Bi.p, n))) return rc;
-    return st->half_sweep(1, it, solver);
+    if ((rc = st->half_sweep(1, it, solver))) return rc;
+    return done();
 }
 
 int CollectiveState::iterate(int niter, bool use_cg, bool finalize_chol)

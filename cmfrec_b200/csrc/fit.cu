@@ -19,6 +19,7 @@
 #include <vector>
 
 #include <chrono>
+#include <csignal>
 #include <cstdlib>
 
 namespace cmfb200 {
@@ -41,6 +42,27 @@ struct StageTimer {
         const auto t1 = std::chrono::steady_clock::now();
         std::fprintf(stderr, "[cmfb200 timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
+    }
+};
+
+// SIGINT between half-sweeps stops the alternation (reference: set_interrup_global_variable / should_stop_procedure,
+// src/helpers.c:1493, polled at src/collective.c:8343, 8612, 8800): the handler is installed for the duration of a fit
+// and the previous one is put back afterwards.
+struct InterruptScope {
+    struct sigaction old_action;
+    bool installed = false;
+    InterruptScope()
+    {
+        stop_flag() = 0;
+        struct sigaction sa;
+        std::memset(&sa, 0, sizeof(sa));
+        sa.sa_handler = [](int) { stop_flag() = 1; };
+        sigemptyset(&sa.sa_mask);
+        installed = sigaction(SIGINT, &sa, &old_action) == 0;
+    }
+    ~InterruptScope()
+    {
+        if (installed) sigaction(SIGINT, &old_action, nullptr);
     }
 };
 
@@ -81,8 +103,6 @@ int fit_explicit(const ExplicitArgs &a)
         return refuse("scale_bias_const");
     const bool collective = a.U || a.II || a.add_implicit_features;
     if (collective && a.k_main) return refuse("k_main together with side information / implicit features");
-    if (collective && a.precompute_for_predictions)
-        return refuse("precompute_for_predictions together with side information / implicit features");
     if (a.add_implicit_features && (!a.Ai || !a.Bi)) return 2;
     if ((a.U && !a.C) || (a.II && !a.D)) return 2;
     if (!a.reset_values) return refuse("reset_values = false");
@@ -172,9 +192,14 @@ int fit_explicit(const ExplicitArgs &a)
         if ((rc = st.upload_bias(2, a.biasB))) return rc;   // left as the caller passed it (src/collective.c:8184)
     }
     tm.lap("upload factors");
+    InterruptScope interrupt_scope;
+    st.verbose = a.verbose;
+    bool interrupted = false;
+    if (a.verbose) { std::printf("Starting ALS optimization routine\n\n"); std::fflush(stdout); }
     if (!collective) {
         rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
-        if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+        if (rc == 3) interrupted = true;
+        else if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
     } else {
         // side information: column-centre (U_colmeans / I_colmeans are outputs), then the C, D, Bi, Ai, B, A loop
         real_t w_user = a.w_user, w_item = a.w_item, w_imp = a.w_implicit;
@@ -202,7 +227,8 @@ int fit_explicit(const ExplicitArgs &a)
         CollectiveState cs;
         if ((rc = cs.setup(&st, cc, Uc.data(), Ic.data()))) return rc;
         rc = cs.iterate(a.niter, use_cg, finalize_chol);
-        if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+        if (rc == 3) interrupted = true;
+        else if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
         if ((rc = cs.download(a.C, a.D, a.Ai, a.Bi))) return rc;
     }
     tm.lap("ALS iterations");
@@ -210,24 +236,44 @@ int fit_explicit(const ExplicitArgs &a)
     if (rc) return rc;
     if (cudaStreamSynchronize(nullptr) != cudaSuccess) return 1;
     tm.lap("download factors");
-
-    if (a.precompute_for_predictions) {
+    if (a.verbose && !interrupted) {
+        std::printf(std::isnan((double)a.A[0]) ? "ALS procedure failed\n" : "ALS procedure terminated successfully\n");
+        std::fflush(stdout);
+    }
+    // an interrupted fit still finishes the precomputed matrices when asked to handle the interrupt
+    // (src/collective.c:8890-8897), and reports code 3 either way
+    if (a.precompute_for_predictions && (!interrupted || a.handle_interrupt)) {
         PostfitExplicit pf;
         pf.B = a.B; pf.biasB = a.item_bias ? a.biasB : nullptr; pf.n = n; pf.kk = kk;
         pf.user_bias = a.user_bias; pf.item_bias = a.item_bias;
         pf.lam = lam_u[2]; pf.lam_bias = lam_u[0]; pf.scale_lam = scale_lam;
         pf.B_plus_bias = a.B_plus_bias; pf.BtB = a.precomputedBtB; pf.TransBtBinvBt = a.precomputedTransBtBinvBt;
+        if (collective) {
+            real_t w_user = a.w_user, w_imp = a.w_implicit;
+            if (a.w_main != 1) { w_user /= a.w_main; w_imp /= a.w_main; }
+            pf.C = a.U ? a.C : nullptr; pf.p = a.U ? a.p : 0; pf.w_user = w_user;
+            pf.Bi = a.add_implicit_features ? a.Bi : nullptr; pf.implicit_features = a.add_implicit_features; pf.w_implicit = w_imp;
+            pf.scale_lam_sideinfo = a.scale_lam_sideinfo;
+            pf.BiTBi = a.precomputedBiTBi; pf.TransCtCinvCt = a.precomputedTransCtCinvCt; pf.CtCw = a.precomputedCtCw;
+            pf.BeTBeChol = a.precomputedBeTBeChol;
+        }
         rc = postfit_explicit(pf);
         if (rc) return rc;
     }
-    return 0;
+    return interrupted ? 3 : 0;
 }
 
 int fit_implicit(const ImplicitArgs &a)
 {
     if (a.k_user && a.U == nullptr && a.nnz_U == 0) return 2;
     if (a.k_item && a.II == nullptr && a.nnz_I == 0) return 2;
-    if (a.U || a.II || a.nnz_U || a.nnz_I) return refuse("side information (U / I)");
+    if (a.nnz_U || a.nnz_I) return refuse("sparse side information (U_sp / I_sp)");
+    if (a.NA_as_zero_U || a.NA_as_zero_I) return refuse("NA_as_zero_U / NA_as_zero_I");
+    if (a.U && a.m_u != a.m) return refuse("side information U with a different number of rows than X");
+    if (a.II && a.n_i != a.n) return refuse("side information I with a different number of rows than X has columns");
+    if ((a.U && !a.C) || (a.II && !a.D)) return 2;
+    const bool collective = a.U || a.II;
+    if (collective && a.k_main) return refuse("k_main together with side information");
     if (a.nonneg || a.nonneg_C || a.nonneg_D) return refuse("non-negativity constraints");
     if (a.l1_lam != 0 || a.l1_lam_unique) return refuse("L1 regularisation");
     if (a.precondition_cg) return refuse("precondition_cg");
@@ -244,9 +290,10 @@ int fit_implicit(const ImplicitArgs &a)
 
     StageTimer tm;
     // starting point on a host thread: A uniform (normal for tiny problems), B zero with CG (src/collective.c:9750-9774)
+    const bool fill_B = a.II != nullptr;   // src/collective.c:9752
     std::thread rng([&]() {
-        random_init(a.A, (size_t)m * kk, nullptr, 0, a.seed, false);
-        if (use_cg) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
+        random_init(a.A, (size_t)m * kk, fill_B ? a.B : nullptr, fill_B ? (size_t)n * kk : 0, a.seed, false);
+        if (use_cg && !fill_B) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
 
@@ -269,8 +316,14 @@ int fit_implicit(const ImplicitArgs &a)
     if (a.w_main_multiplier) *a.w_main_multiplier = mult;
     real_t lamA = a.lam_unique ? a.lam_unique[2] : a.lam;
     real_t lamB = a.lam_unique ? a.lam_unique[3] : a.lam;
+    real_t lamC = a.lam_unique ? a.lam_unique[4] : a.lam;
+    real_t lamD = a.lam_unique ? a.lam_unique[5] : a.lam;
     real_t lam_plain = a.lam;
-    if (w_main != 1) { lamA /= w_main; lamB /= w_main; lam_plain /= w_main; }
+    real_t w_user = a.w_user, w_item = a.w_item;
+    if (w_main != 1) {
+        lamA /= w_main; lamB /= w_main; lamC /= w_main; lamD /= w_main; lam_plain /= w_main;
+        w_user /= w_main; w_item /= w_main;
+    }
 
     AlsConfig cfg;
     cfg.implicit = true;
@@ -288,20 +341,61 @@ int fit_implicit(const ImplicitArgs &a)
     tm.lap("upload COO + CSR/CSC (GPU)");
     rng.join();
     tm.lap("factor initialisation (host)");
-    rc = st.upload_coordinates(a.A, use_cg ? nullptr : a.B);
+    rc = st.upload_coordinates(a.A, (use_cg && !fill_B) ? nullptr : a.B);
     if (rc) return rc;
-    rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
-    if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    InterruptScope interrupt_scope;
+    st.verbose = a.verbose;
+    bool interrupted = false;
+    if (a.verbose) { std::printf("Starting ALS optimization routine\n\n"); std::fflush(stdout); }
+    if (!collective) {
+        rc = st.iterate(0, a.niter, a.niter, use_cg, finalize_chol);
+        if (rc == 3) interrupted = true;
+        else if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+    } else {
+        // implicit feedback + dense side information (src/collective.c:9832-10022: C, D, then B and A through
+        // optimizeA_collective_implicit): column-centre U / I, then the same machinery as the explicit collective model
+        if (cfg.world > 1) return refuse("side information on more than one GPU");
+        std::vector<real_t> Uc, Ic;
+        CollectiveConfig cc;
+        if (a.U) {
+            cc.p = a.p;
+            if (a.U_colmeans) { if (center_side_info(a.U, m, a.p, a.U_colmeans, Uc)) return refuse("missing values in U"); }
+            else Uc.assign(a.U, a.U + (size_t)m * a.p);
+        }
+        if (a.II) {
+            cc.q = a.q;
+            if (a.I_colmeans) { if (center_side_info(a.II, n, a.q, a.I_colmeans, Ic)) return refuse("missing values in I"); }
+            else Ic.assign(a.II, a.II + (size_t)n * a.q);
+        }
+        for (real_t v : Uc) if (std::isnan(v)) return refuse("missing values in U");
+        for (real_t v : Ic) if (std::isnan(v)) return refuse("missing values in I");
+        cc.w_user = w_user; cc.w_item = w_item;
+        cc.lam_C = lamC / w_user;
+        cc.lam_D = lamD / w_item;
+        CollectiveState cs;
+        if ((rc = cs.setup(&st, cc, Uc.data(), Ic.data()))) return rc;
+        rc = cs.iterate(a.niter, use_cg, finalize_chol);
+        if (rc == 3) interrupted = true;
+        else if (rc) return rc == 2 ? refuse("this solver / k combination") : rc;
+        if ((rc = cs.download(a.C, a.D, nullptr, nullptr))) return rc;
+    }
     tm.lap("ALS iterations");
     rc = st.download_factors(a.A, kk, nullptr, a.B, kk, nullptr);
     if (rc) return rc;
     tm.lap("download factors");
 
-    if (a.precompute_for_predictions && a.precomputedBtB) {
-        // BtB + lam*I (src/collective.c:10057-10074)
-        postfit_implicit(a.B, n, kk, lam_plain, a.precomputedBtB);
+    if (a.verbose && !interrupted) {
+        std::printf(std::isnan((double)a.A[0]) ? "ALS procedure failed\n" : "ALS procedure terminated successfully\n");
+        std::fflush(stdout);
     }
-    return 0;
+    if (a.precompute_for_predictions && (!interrupted || a.handle_interrupt)) {
+        // BtB + lam*I (src/collective.c:10057-10074); with user side information also BeTBe and its Cholesky factor
+        if (a.verbose) { std::printf("Finishing precomputed matrices..."); std::fflush(stdout); }
+        postfit_implicit(a.B, n, kk, lam_plain, a.precomputedBtB, a.U ? a.C : nullptr, a.U ? a.p : 0, w_user, a.precomputedBeTBe,
+                         a.precomputedBeTBeChol, use_cg && !finalize_chol);
+        if (a.verbose) { std::printf("  done\n"); std::fflush(stdout); }
+    }
+    return interrupted ? 3 : 0;
 }
 
 }  // namespace cmfb200

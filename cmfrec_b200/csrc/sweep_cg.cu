@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) cg_sweep_kernel(con
             const size_t beg = p.X.ptr[row];
             const int nnz = (int)(p.X.ptr[row + 1] - beg);
             CgRow<T, C, L, MODEL, W, GRAM_SMEM> s(p, scratch_team, gram, w, 0);
-            if (nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows)) {
+            if (nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows)) {
                 DirectGather<T, C, L, W> gat(p, w);
                 gat.beg = beg; gat.nnz = nnz;
                 s.solve(row, nnz, gat);
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) cg_sweep_kernel(con
                 const size_t beg = p.X.ptr[row];
                 const int nnz = (int)(p.X.ptr[row + 1] - beg);
                 CgRow<T, C, L, MODEL, 1, GRAM_SMEM> s(p, scratch_warp + w * TeamScratch<T, C, L, 1>::elems(), gram, 0, 0);
-                if (nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows)) {
+                if (nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows)) {
                     DirectGather<T, C, L, 1> gat(p, 0);
                     gat.beg = beg; gat.nnz = nnz;
                     s.solve(row, nnz, gat);

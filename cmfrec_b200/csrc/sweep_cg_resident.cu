@@ -310,7 +310,7 @@ __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, si
     // one named barrier per (team size, team): a block's teams run ahead of each other by whole slots
     const int bar_id = (TW == 8) ? 1 : (TW == 4) ? 2 + team : (TW == 2) ? 4 + team : 0;
     CgRow<T, C, L, MODEL, TW, GRAM_SMEM> s(p, stripes + (size_t)(team * TW) * ResidentSmem<T, C, L>::STRIPE, gram, wt, bar_id);
-    if (nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows)) {
+    if (nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows)) {
         Gat gat(p, region, cap, wt, TW);
         gat.begin(beg, nnz);
         gat.stage();

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
         const size_t beg = p.X.ptr[row];
         const int nnz = (int)(p.X.ptr[row + 1] - beg);
         T *frow = p.F + (size_t)row * (size_t)p.ldF;
-        if (nnz <= 0 && !(MODEL == kModelCollective && p.solve_all_rows)) {
+        if (nnz <= 0 && !(MODEL != kModelExplicit && p.solve_all_rows)) {
             if (IMPLICIT || MODEL == kModelCollective) {
                 // implicit: A := 0 up front (src/common.c:3334); collective without any information: zeroed too
                 for (int c = tid; c < kk; c += NT) frow[c] = T(0);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
             }
         }
         if (tid < kd) {
-            if (MODEL == kModelCollective && p.qvec && tid < kk) rhs_acc += p.qvec[(size_t)row * (size_t)p.ldq + tid];
+            if (MODEL != kModelExplicit && p.qvec && tid < kk) rhs_acc += p.qvec[(size_t)row * (size_t)p.ldq + tid];
             rhs[tid] = rhs_acc;
         }
         __syncthreads();

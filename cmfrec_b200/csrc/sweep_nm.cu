@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(kNmThreads, 1) nm_sweep_kernel(const CgSweepPa
             have_nx = nm_row_at(p, i + 1, nx);       // in flight while this row is assembled
             const int nnz = r.nnz;
             float *frow = p.F + (size_t)r.row * (size_t)p.ldF;
-            const bool solve_it = nnz > 0 || (MODEL == kModelCollective && p.solve_all_rows);
+            const bool solve_it = nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows);
             if (!solve_it) {
                 if (IMPLICIT || MODEL == kModelCollective) {
                     // implicit: A := 0 up front (src/common.c:3334); collective without any information: zeroed too
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(kNmThreads, 1) nm_sweep_kernel(const CgSweepPa
                 if (lane == 0) bars.red[q] = sx;
             }
             for (int cc = tid; cc < kk; cc += GT) {
-                if (MODEL == kModelCollective && p.qvec) M[(size_t)n * S::MS + cc] += p.qvec[(size_t)r.row * (size_t)p.ldq + cc];
+                if (MODEL != kModelExplicit && p.qvec) M[(size_t)n * S::MS + cc] += p.qvec[(size_t)r.row * (size_t)p.ldq + cc];
                 if (hb && !CHOL) M[(size_t)cc * S::MS + kk] = M[(size_t)kk * S::MS + cc];   // CG reads whole rows
                 if (CHOL) M[(size_t)cc * S::MS + cc] += lam;
             }

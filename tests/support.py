@@ -76,22 +76,30 @@ def fit_explicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=0.05, user_bias=True, 
     Bi = np.zeros((n, k), dt) if add_implicit_features else None
     Ucm = np.zeros(p, dt) if (p and center_side) else None
     Icm = np.zeros(q, dt) if (q and center_side) else None
+    collective = bool(p or q or add_implicit_features)
+    BiTBi = np.zeros((kk, kk), dt) if (precompute and add_implicit_features) else None
+    TCt = np.zeros((p, kk), dt) if (precompute and p) else None
+    CtCw = np.zeros((kk, kk), dt) if (precompute and p) else None
+    BeChol = np.zeros((kk + ub, kk + ub), dt) if (precompute and collective) else None
     rc = lib.fit_collective_explicit_als(
         ptr(biasA) if user_bias else None, ptr(biasB) if item_bias else None, ptr(A), ptr(B), ptr(C), ptr(D), ptr(Ai), ptr(Bi),
         add_implicit_features, True, seed, ptr(glob_mean), ptr(Ucm), ptr(Icm), m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size,
         None, None, user_bias, item_bias, center, lam, ptr(lu), 0.0, None, scale_lam, False, False, ptr(sA), ptr(sB),
         ptr(Uc), m if p else 0, p, ptr(Ic), n if q else 0, q, None, None, None, 0, None, None, None, 0, False, False, False,
         k_main, 0, 0, w_main, w_user, w_item, w_implicit, niter, nthreads, False, False, use_cg, max_cg_steps, False,
-        finalize_chol, False, 100, False, False, precompute, True, ptr(Bpb), ptr(BtB), ptr(TBt), None, None, None, None, None,
-        None)
+        finalize_chol, False, 100, False, False, precompute, True, ptr(Bpb), ptr(BtB), ptr(TBt), None, ptr(BeChol), ptr(BiTBi),
+        ptr(TCt), ptr(CtCw), None)
     return dict(rc=rc, A=A, B=B, biasA=biasA, biasB=biasB, glob_mean=glob_mean[0], B_plus_bias=Bpb, BtB=BtB,
-                TransBtBinvBt=TBt, C=C, D=D, Ai=Ai, Bi=Bi, U_colmeans=Ucm, I_colmeans=Icm)
+                TransBtBinvBt=TBt, C=C, D=D, Ai=Ai, Bi=Bi, U_colmeans=Ucm, I_colmeans=Icm, BeTBeChol=BeChol, BiTBi=BiTBi,
+                TransCtCinvCt=TCt, CtCw=CtCw)
 
 
 def fit_implicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=5.0, alpha=1.0, niter=3, use_cg=True, max_cg_steps=3,
                  finalize_chol=False, seed=1, nthreads=4, w_main=1.0, adjust_weight=False, apply_log_transf=False,
-                 precompute=False, k_main=0, copy_inputs=True, out=None):
-    """Call fit_collective_implicit_als (reference src/cmfrec.h:1893) on `lib` (copy_inputs / out: see fit_explicit)."""
+                 precompute=False, k_main=0, copy_inputs=True, out=None, U=None, I=None, w_user=1.0, w_item=1.0,
+                 center_side=True, lam_unique=None):
+    """Call fit_collective_implicit_als (reference src/cmfrec.h:1893) on `lib` (copy_inputs / out: see fit_explicit);
+    U [m x p] / I [n x q]: dense side information."""
     dt = np.dtype(dtype)
     kk = k + k_main
     out = out or {}
@@ -103,13 +111,25 @@ def fit_implicit(lib, dtype, ixA, ixB, X, m, n, k, *, lam=5.0, alpha=1.0, niter=
         ixA = np.ascontiguousarray(ixA, np.int32).copy()
         ixB = np.ascontiguousarray(ixB, np.int32).copy()
         X = np.ascontiguousarray(X, dt).copy()
+    p = 0 if U is None else U.shape[1]
+    q = 0 if I is None else I.shape[1]
+    Uc = None if U is None else np.ascontiguousarray(U, dt).copy()
+    Ic = None if I is None else np.ascontiguousarray(I, dt).copy()
+    Cm = np.zeros((p, k), dt) if p else None
+    Dm = np.zeros((q, k), dt) if q else None
+    Ucm = np.zeros(p, dt) if (p and center_side) else None
+    Icm = np.zeros(q, dt) if (q and center_side) else None
+    lu = None if lam_unique is None else np.asarray(lam_unique, dt)
+    BeTBe = np.zeros((kk, kk), dt) if (precompute and p) else None
+    BeChol = np.zeros((kk, kk), dt) if (precompute and p) else None
     rc = lib.fit_collective_implicit_als(
-        ptr(A), ptr(B), None, None, True, seed, None, None, m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size,
-        lam, None, 0.0, None, None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False,
-        k_main, 0, 0, w_main, 1.0, 1.0, ptr(wmm), alpha, adjust_weight, apply_log_transf, niter, nthreads,
+        ptr(A), ptr(B), ptr(Cm), ptr(Dm), True, seed, ptr(Ucm), ptr(Icm), m, n, k, ptr(ixA), ptr(ixB), ptr(X), X.size,
+        lam, ptr(lu), 0.0, None, ptr(Uc), m if p else 0, p, ptr(Ic), n if q else 0, q, None, None, None, 0, None, None, None, 0,
+        False, False, k_main, 0, 0, w_main, w_user, w_item, ptr(wmm), alpha, adjust_weight, apply_log_transf, niter, nthreads,
         False, False, use_cg, max_cg_steps, False, finalize_chol, False, 100, False, False, precompute,
-        ptr(BtB), None, None, None)
-    return dict(rc=rc, A=A, B=B, w_main_multiplier=wmm[0], BtB=BtB)
+        ptr(BtB), ptr(BeTBe), ptr(BeChol), None)
+    return dict(rc=rc, A=A, B=B, w_main_multiplier=wmm[0], BtB=BtB, C=Cm, D=Dm, U_colmeans=Ucm, I_colmeans=Icm, BeTBe=BeTBe,
+                BeTBeChol=BeChol)
 
 
 def csr_csc(lib, dtype, ixA, ixB, X, m, n):

@@ -166,6 +166,63 @@ def test_implicit_fit_matches_reference(gpu_libs, dtype, case):
     assert abs(fa - fb) <= 1e-3 * abs(fb), (fa, fb)
 
 
+CASES_IMPLICIT_SIDE = [
+    dict(side="UI"),                                      # CG, both matrices
+    dict(side="UI", use_cg=False),                        # Cholesky throughout
+    dict(side="U", finalize_chol=True, w_user=2.5),
+    dict(side="I", w_item=0.4, alpha=10.0, lam=1.0),
+    dict(side="UI", w_main=2.0, lam_unique=[0, 0, 3.0, 4.0, 1.5, 2.5], center_side=False),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", range(len(CASES_IMPLICIT_SIDE)))
+@pytest.mark.parametrize("niter", [1, 3])
+def test_implicit_side_information_matches_reference(gpu_libs, dtype, case, niter):
+    """Implicit feedback WITH dense side information: fit_collective_implicit_als with U / I against the
+    reference (optimizeA_collective_implicit src/collective.c:5971, collective_block_cg_implicit :2905,
+    collective_closed_form_block_implicit :1849).  niter = 1 is exactly one call of each per side from the
+    bit-identical starting point (the per-half-sweep comparison); zero-mean-ish side information keeps the systems
+    well conditioned, so float32 is held to 1e-3 of max|F| on 99 % of the rows."""
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    kw = dict(niter=niter, nthreads=4)
+    kw.update(CASES_IMPLICIT_SIDE[case])
+    side = kw.pop("side")
+    m, n, k = 20000, 9000, 16          # > 2^18 factor entries: the uniform initialiser (Q7)
+    ixA, ixB, X = synth_coo(m, n, 150000, dt, seed=60 + case, kind="counts")
+    rng = np.random.default_rng(case)
+    if "U" in side:
+        kw["U"] = rng.normal(size=(m, 6)).astype(dt) + 0.3
+    if "I" in side:
+        kw["I"] = rng.normal(size=(n, 5)).astype(dt) - 0.2
+    a = fit_implicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+    b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+    assert a["rc"] == 0 and b["rc"] == 0
+    for key in ("U_colmeans", "I_colmeans"):
+        if b[key] is not None:
+            assert np.array_equal(a[key], b[key]), key
+    if dt == np.float64:
+        for key in ("C", "D", "B", "A"):
+            if b[key] is not None:
+                assert rows_match(a[key], b[key], 1e-7, 0.01), (key, rel_err(a[key], b[key]))
+        return
+    # float32: the fit starts from all-positive uniform factors (ill conditioned, and the truncated CG amplifies it through
+    # the alternation), so the GPU is held to the reference's OWN float32 accuracy: row errors against the float64
+    # reference fit no larger than 3x those of the float32 reference fit, at the median / 90th / 99th percentile
+    R64 = _ref(np.float64)
+    kw64 = {key: (np.asarray(v, np.float64) if isinstance(v, np.ndarray) else v) for key, v in kw.items()}
+    e = fit_implicit(R64, np.float64, ixA, ixB, X.astype(np.float64), m, n, k, **kw64)
+    for key in ("C", "D", "B", "A"):
+        if b[key] is None:
+            continue
+        scale = np.abs(e[key]).max()
+        e_gpu = np.abs(a[key].astype(np.float64) - e[key]).max(axis=1) / scale
+        e_ref = np.abs(b[key].astype(np.float64) - e[key]).max(axis=1) / scale
+        qs = [0.5, 0.9, 0.99] if a[key].shape[0] > 100 else [0.5, 1.0]
+        assert (np.quantile(e_gpu, qs) <= 3 * np.quantile(e_ref, qs) + 1e-4).all(), (key, np.quantile(e_gpu, qs), np.quantile(e_ref, qs))
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_precomputed_outputs(gpu_libs, dtype):
     """precompute_for_predictions: B_plus_bias, BtB (upper triangle), TransBtBinvBt (src/collective.c:8935-9075)"""
@@ -185,6 +242,88 @@ def test_precomputed_outputs(gpu_libs, dtype):
     a = fit_implicit(L, dt, ixA, ixB, X, m, n, k, niter=2, precompute=True)
     b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, niter=2, precompute=True)
     assert rel_err(a["BtB"][np.triu_indices(k)], b["BtB"][np.triu_indices(k)]) <= tol
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", ["UI", "U_implicit_features", "implicit_feedback_U"])
+def test_precomputed_outputs_collective(gpu_libs, dtype, case):
+    """precompute_for_predictions (the Python default) with side information / implicit features: BtB, BiTBi, CtCw,
+    TransCtCinvCt, TransBtBinvBt, BeTBeChol (src/collective.c:8935-9255); implicit feedback with U: BtB, BeTBe, BeTBeChol
+    (:10055-10105).  Upper triangles are what the reference defines."""
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    m, n, k = 900, 500, 10
+    rng = np.random.default_rng(3)
+    U = rng.normal(size=(m, 6)).astype(dt); I = rng.normal(size=(n, 4)).astype(dt)
+    tol = 1e-6 if dt == np.float64 else 5e-3
+    iu = np.triu_indices(k + 1)
+    ik = np.triu_indices(k)
+    if case == "implicit_feedback_U":
+        ixA, ixB, X = synth_coo(m, n, 20000, dt, seed=81, kind="counts")
+        kw = dict(niter=2, precompute=True, U=U, w_user=1.5)
+        a = fit_implicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+        b = fit_implicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+        assert a["rc"] == 0 and b["rc"] == 0
+        for key in ("BtB", "BeTBe", "BeTBeChol"):
+            assert rel_err(a[key][ik], b[key][ik]) <= tol, key
+        return
+    ixA, ixB, X = synth_coo(m, n, 20000, dt, seed=80)
+    kw = dict(lam=0.8, niter=2, precompute=True, finalize_chol=True, U=U, w_user=1.5)
+    if case == "UI":
+        kw["I"] = I
+    else:
+        kw.update(add_implicit_features=True, w_implicit=0.5)
+    a = fit_explicit(L, dt, ixA, ixB, X, m, n, k, **kw)
+    b = fit_explicit(R, dt, ixA, ixB, X, m, n, k, **kw)
+    assert a["rc"] == 0 and b["rc"] == 0
+    assert rel_err(a["BtB"][iu], b["BtB"][iu]) <= tol
+    assert rel_err(a["CtCw"][ik], b["CtCw"][ik]) <= tol
+    assert rel_err(a["BeTBeChol"][iu], b["BeTBeChol"][iu]) <= tol
+    if case == "UI":
+        assert rel_err(a["TransBtBinvBt"], b["TransBtBinvBt"]) <= tol
+        assert rel_err(a["TransCtCinvCt"], b["TransCtCinvCt"]) <= tol
+    else:
+        assert rel_err(a["BiTBi"][ik], b["BiTBi"][ik]) <= tol
+
+
+def test_interrupt_returns_code_3(gpu_libs):
+    """SIGINT during the alternation: the fit stops between half-sweeps and returns 3 (reference src/collective.c:8890,
+    src/helpers.c:1493); the previous handler is put back afterwards."""
+    import os, signal, threading, time
+    dt = np.dtype(np.float32)
+    L = gpu_libs[dt]
+    m, n, k = 20000, 8000, 32
+    ixA, ixB, X = synth_coo(m, n, 600000, dt, seed=9)
+    assert fit_explicit(L, dt, ixA, ixB, X, m, n, k, niter=1)["rc"] == 0       # warm the pools
+    before = signal.getsignal(signal.SIGINT)
+    threading.Timer(0.5, lambda: os.kill(os.getpid(), signal.SIGINT)).start()
+    t0 = time.time()
+    try:
+        out = fit_explicit(L, dt, ixA, ixB, X, m, n, k, niter=1000000)
+    except KeyboardInterrupt:                      # raised by Python's own handler if the signal landed outside the call
+        pytest.fail("the signal was not handled inside the fit")
+    assert out["rc"] == 3 and time.time() - t0 < 30
+    assert np.isfinite(out["A"]).all()
+    assert signal.getsignal(signal.SIGINT) is before
+
+
+def test_verbose_prints_the_references_progress_lines(gpu_libs, capfd):
+    dt = np.dtype(np.float64)
+    L = gpu_libs[dt]
+    from support import ptr
+    m, n, k = 400, 300, 6
+    ixA, ixB, X = synth_coo(m, n, 5000, dt, seed=2)
+    A = np.zeros((m, k)); B = np.zeros((n, k)); bA = np.zeros(m); bB = np.zeros(n); g = np.zeros(1); s1 = np.zeros(1); s2 = np.zeros(1)
+    rc = L.fit_collective_explicit_als(
+        ptr(bA), ptr(bB), ptr(A), ptr(B), None, None, None, None, False, True, 1, ptr(g), None, None, m, n, k,
+        ptr(ixA), ptr(ixB), ptr(X), X.size, None, None, True, True, True, 1.0, None, 0.0, None, False, False, False,
+        ptr(s1), ptr(s2), None, 0, 0, None, 0, 0, None, None, None, 0, None, None, None, 0, False, False, False,
+        0, 0, 0, 1.0, 1.0, 1.0, 1.0, 2, 1, True, False, True, 3, False, False, False, 100, False, False, False, True,
+        None, None, None, None, None, None, None, None, None)
+    assert rc == 0
+    text = capfd.readouterr().out
+    assert "Starting ALS optimization routine" in text and text.count("Updating B ... done") == 2
+    assert "Completed ALS iteration  2" in text and "ALS procedure terminated successfully" in text
 
 
 def test_unsupported_arguments_are_refused(gpu_libs):
