@@ -67,6 +67,9 @@ int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream);
 // return 3 when the shape is not covered (nothing launched).  The launchers above try these first (CMFB200_NM=0: never).
 int launch_explicit_chol_sweep_nm(const CgSweepParams &p, cudaStream_t stream);
 int launch_implicit_chol_sweep_nm(const CgSweepParams &p, cudaStream_t stream);
+// the same on the FP64 tensor cores (sweep_chol_dmma.cu; fp64 library, k + bias + 1 <= 136); 3 = not covered
+int launch_explicit_chol_sweep_dmma(const CgSweepParams &p, cudaStream_t stream);
+int launch_implicit_chol_sweep_dmma(const CgSweepParams &p, cudaStream_t stream);
 // explicit / collective model, k <= 64: the reference's truncated CG run on the tensor-core-built normal matrix (one
 // gather per stored entry instead of one per CG pass); 3 = not covered
 int launch_explicit_cg_sweep_nm(const CgSweepParams &p, cudaStream_t stream);

@@ -340,10 +340,20 @@ static bool nm_enabled()
     return e ? std::atoi(e) != 0 : true;
 }
 
+static bool dmma_enabled()
+{
+    const char *e = std::getenv("CMFB200_DMMA");
+    return e ? std::atoi(e) != 0 : true;
+}
+
 int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream)
 {
     if (nm_enabled()) {
         const int rc = launch_explicit_chol_sweep_nm(p, stream);
+        if (rc != 3) return rc;
+    }
+    if (dmma_enabled()) {
+        const int rc = launch_explicit_chol_sweep_dmma(p, stream);
         if (rc != 3) return rc;
     }
     return (p.gram || p.qvec || p.solve_all_rows) ? dispatch_chol<kModelCollective>(p, stream)
@@ -353,6 +363,10 @@ int launch_implicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream)
 {
     if (nm_enabled()) {
         const int rc = launch_implicit_chol_sweep_nm(p, stream);
+        if (rc != 3) return rc;
+    }
+    if (dmma_enabled()) {
+        const int rc = launch_implicit_chol_sweep_dmma(p, stream);
         if (rc != 3) return rc;
     }
     return dispatch_chol<kModelImplicit>(p, stream);

@@ -10,4 +10,6 @@ env "${envs[@]}" timeout 900 ncu --set full --clock-control none --import-source
 ncu -i /tmp/$tag.ncu-rep --page raw --csv > gpurun_out/ncu/$tag.raw.csv 2>/dev/null
 ncu -i /tmp/$tag.ncu-rep --page source --csv --print-source sass > gpurun_out/ncu/$tag.src.csv 2>/dev/null
 gzip -f gpurun_out/ncu/$tag.src.csv
+ncu -i /tmp/$tag.ncu-rep --page source --csv --print-source cuda > gpurun_out/ncu/$tag.cuda.csv 2>/dev/null
+gzip -f gpurun_out/ncu/$tag.cuda.csv
 ls -la gpurun_out/ncu/
