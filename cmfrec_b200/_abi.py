@@ -108,13 +108,15 @@ def als_options_type(real):
 
 
 REFERENCE_ENTRY_POINTS = ("fit_collective_explicit_als", "fit_collective_implicit_als", "fit_most_popular", "topN",
-                          "get_has_openmp")
+                          "get_has_openmp", "predict_multiple", "predict_X_old_collective_explicit",
+                          "predict_X_old_collective_implicit", "topN_old_collective_explicit", "topN_old_collective_implicit")
 
 PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
     "cmfb200_real_name", "cmfb200_device_count", "cmfb200_random_init", "cmfb200_coo_to_csr_and_csc",
     "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_partition_rows", "cmfb200_nccl_unique_id", "cmfb200_als_create",
     "cmfb200_gram", "cmfb200_set_world", "cmfb200_trim_pool", "cmfb200_debug_poison_smem", "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
     "cmfb200_als_iterate", "cmfb200_als_timed_iterate", "cmfb200_als_set_profile",
+    "cmfb200_serve_create", "cmfb200_serve_destroy", "cmfb200_serve_predict", "cmfb200_serve_topn", "cmfb200_gemm_nt",
     "cmfb200_als_read_profile", "cmfb200_als_attach_collective", "cmfb200_als_get_collective", "cmfb200_als_sync", "cmfb200_als_launch_count", "cmfb200_als_local_counts",
 )
 
@@ -132,6 +134,19 @@ def bind_reference_names(lib, dtype):
     lib.topN.restype = c_int
     lib.get_has_openmp.argtypes = []
     lib.get_has_openmp.restype = c_bool
+    P = _P()
+    # reference src/cmfrec.h: predict_multiple returns void there; the product returns its error code
+    lib.predict_multiple.argtypes = [P, c_int, P, c_int, P, P, real, c_int, c_int, c_int, c_int, P, P, c_size_t, P, c_int]
+    lib.predict_multiple.restype = c_int
+    lib.predict_X_old_collective_explicit.argtypes = [P, P, P, c_size_t, P, P, P, P, real, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.predict_X_old_collective_explicit.restype = c_int
+    lib.predict_X_old_collective_implicit.argtypes = [P, P, P, c_size_t, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.predict_X_old_collective_implicit.restype = c_int
+    lib.topN_old_collective_explicit.argtypes = [P, real, P, P, c_int, P, P, real, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P,
+                                                 c_int, c_int, c_int, c_bool, c_int]
+    lib.topN_old_collective_explicit.restype = c_int
+    lib.topN_old_collective_implicit.argtypes = [P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int]
+    lib.topN_old_collective_implicit.restype = c_int
     return lib
 
 
@@ -163,6 +178,16 @@ def bind_product(lib, dtype):
     lib.cmfb200_gram.argtypes = [P, c_int, c_int, P, c_int, C.POINTER(C.c_float)]
     lib.cmfb200_trim_pool.restype = None
     lib.cmfb200_trim_pool.argtypes = []
+    lib.cmfb200_serve_create.restype = c_void_p
+    lib.cmfb200_serve_create.argtypes = [P, c_int, c_int, P, c_int, c_int, P, P, real, c_int, c_int, C.POINTER(c_int)]
+    lib.cmfb200_serve_destroy.restype = None
+    lib.cmfb200_serve_destroy.argtypes = [P]
+    lib.cmfb200_serve_predict.restype = c_int
+    lib.cmfb200_serve_predict.argtypes = [P, P, P, c_size_t, P]
+    lib.cmfb200_serve_topn.restype = c_int
+    lib.cmfb200_serve_topn.argtypes = [P, P, c_int, P, P, c_int, P, P, C.POINTER(C.c_float)]
+    lib.cmfb200_gemm_nt.restype = c_int
+    lib.cmfb200_gemm_nt.argtypes = [P, c_int, c_int, P, c_int, c_int, c_int, P, c_int, C.POINTER(C.c_float)]
     lib.cmfb200_set_world.restype = C.c_int
     lib.cmfb200_set_world.argtypes = [C.c_int, C.c_int, C.c_void_p]
     lib.cmfb200_debug_poison_smem.restype = C.c_int

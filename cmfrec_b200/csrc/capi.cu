@@ -11,6 +11,9 @@
 #include "nccl_link.h"
 #include "popular.h"
 #include "topn.h"
+#include "serve.h"
+#include "gemm_tc.h"
+#include <cmath>
 
 using namespace cmfb200;
 
@@ -84,6 +87,111 @@ int topN(real_t *a_vec, int_t k_user, real_t *B, int_t k_item, real_t *biasB, re
 {
     return top_n(a_vec, k_user, B, k_item, biasB, glob_mean, biasA, k, k_main, include_ix, n_include, exclude_ix,
                  n_exclude, outp_ix, outp_score, n_top, n, nthreads);
+}
+
+int predict_multiple(real_t *A, int_t k_user, real_t *B, int_t k_item, real_t *biasA, real_t *biasB, real_t glob_mean, int_t k,
+                     int_t k_main, int_t m, int_t n, int_t predA[], int_t predB[], size_t nnz, real_t *outp, int nthreads)
+{
+    (void)nthreads;
+    return predict_multiple_host(A, k_user, B, k_item, biasA, biasB, glob_mean, k, k_main, m, n, predA, predB, nnz, outp);
+}
+
+// reference src/collective.c:11797-11835: unknown ids fall back to mean + whatever bias is known
+int predict_X_old_collective_explicit(int_t row[], int_t col[], real_t *predicted, size_t n_predict, real_t *A, real_t *biasA,
+                                      real_t *B, real_t *biasB, real_t glob_mean, int_t k, int_t k_user, int_t k_item, int_t k_main,
+                                      int_t m, int_t n_max, int nthreads)
+{
+    (void)nthreads;
+    const int rc = predict_multiple_host(A, k_user, B, k_item, biasA, biasB, glob_mean, k, k_main, m, n_max, row, col, n_predict, predicted);
+    if (rc) return rc;
+    for (size_t ix = 0; ix < n_predict; ix++)
+        if (std::isnan(predicted[ix]))
+            predicted[ix] = glob_mean + ((biasA != nullptr && row[ix] < m) ? biasA[row[ix]] : real_t(0)) +
+                            ((biasB != nullptr && col[ix] < n_max) ? biasB[col[ix]] : real_t(0));
+    return 0;
+}
+
+// reference src/collective.c:11837-11862
+int predict_X_old_collective_implicit(int_t row[], int_t col[], real_t *predicted, size_t n_predict, real_t *A, real_t *B, int_t k,
+                                      int_t k_user, int_t k_item, int_t k_main, int_t m, int_t n, int nthreads)
+{
+    (void)nthreads;
+    return predict_multiple_host(A, k_user, B, k_item, nullptr, nullptr, real_t(0), k, k_main, m, n, row, col, n_predict, predicted);
+}
+
+// reference src/collective.c:11546-11587
+int topN_old_collective_explicit(real_t *a_vec, real_t a_bias, real_t *A, real_t *biasA, int_t row_index, real_t *B, real_t *biasB,
+                                 real_t glob_mean, int_t k, int_t k_user, int_t k_item, int_t k_main, int_t *include_ix, int_t n_include,
+                                 int_t *exclude_ix, int_t n_exclude, int_t *outp_ix, real_t *outp_score, int_t n_top, int_t n, int_t n_max,
+                                 bool include_all_X, int nthreads)
+{
+    if (include_all_X || n == 0) n = n_max;
+    if (a_vec != nullptr)
+        return top_n(a_vec, k_user, B, k_item, biasB, glob_mean, a_bias, k, k_main, include_ix, n_include, exclude_ix, n_exclude, outp_ix,
+                     outp_score, n_top, n, nthreads);
+    return top_n(A + (size_t)row_index * (size_t)(k_user + k + k_main), k_user, B, k_item, biasB, glob_mean,
+                 biasA == nullptr ? real_t(0) : biasA[row_index], k, k_main, include_ix, n_include, exclude_ix, n_exclude, outp_ix, outp_score,
+                 n_top, n, nthreads);
+}
+
+// reference src/collective.c:11589-11614
+int topN_old_collective_implicit(real_t *a_vec, real_t *A, int_t row_index, real_t *B, int_t k, int_t k_user, int_t k_item, int_t k_main,
+                                 int_t *include_ix, int_t n_include, int_t *exclude_ix, int_t n_exclude, int_t *outp_ix, real_t *outp_score,
+                                 int_t n_top, int_t n, int nthreads)
+{
+    return topN_old_collective_explicit(a_vec, real_t(0), A, nullptr, row_index, B, nullptr, real_t(0), k, k_user, k_item, k_main, include_ix,
+                                        n_include, exclude_ix, n_exclude, outp_ix, outp_score, n_top, n, n, false, nthreads);
+}
+
+// ---- batched serving from factors resident in HBM (serve.cu)
+void *cmfb200_serve_create(const real_t *A, int_t m, int_t k_user, const real_t *B, int_t n, int_t k_item, const real_t *biasA,
+                           const real_t *biasB, real_t glob_mean, int_t k, int_t k_main, int *rc_out)
+{
+    int rc = 0;
+    cmfb200::ServeState *s = cmfb200::serve_create(A, m, k_user, B, n, k_item, biasA, biasB, glob_mean, k, k_main, &rc);
+    if (rc_out) *rc_out = rc;
+    return s;
+}
+void cmfb200_serve_destroy(void *h) { cmfb200::serve_destroy(static_cast<cmfb200::ServeState *>(h)); }
+int cmfb200_serve_predict(void *h, const int_t *row, const int_t *col, size_t n_predict, real_t *out)
+{
+    return h ? cmfb200::serve_predict(static_cast<cmfb200::ServeState *>(h), row, col, n_predict, out) : 2;
+}
+int cmfb200_serve_topn(void *h, const int_t *users, int_t n_users, const size_t *seen_ptr, const int_t *seen_idx, int_t n_top,
+                       int_t *out_ix, real_t *out_score, float *ms_device)
+{
+    return h ? cmfb200::serve_topn(static_cast<cmfb200::ServeState *>(h), users, n_users, seen_ptr, seen_idx, n_top, out_ix, out_score, ms_device)
+             : 2;
+}
+
+// C[M x N] = A[M x K] B[N x K]^T on the tensor cores, host buffers in / out (test and measurement aid for gemm_tc.cu)
+int cmfb200_gemm_nt(const real_t *A, int lda, int M, const real_t *B, int ldb, int N, int K, real_t *C, int repeats, float *ms_per_launch)
+{
+    using namespace cmfb200;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return 1;
+    DevBuf<real_t> dA, dB, dC;
+    if (!dA.alloc((size_t)M * lda + 4) || !dB.alloc((size_t)N * ldb + 4) || !dC.alloc((size_t)M * N)) return 1;
+    cudaMemcpy(dA.p, A, (size_t)M * lda * sizeof(real_t), cudaMemcpyHostToDevice);
+    cudaMemcpy(dB.p, B, (size_t)N * ldb * sizeof(real_t), cudaMemcpyHostToDevice);
+    int rc = launch_gemm_nt_tc(dA.p, lda, M, dB.p, ldb, N, K, dC.p, N, nullptr, nullptr, real_t(0), nullptr);
+    if (rc) return rc;
+    if (repeats > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, nullptr);
+        for (int i = 0; i < repeats; i++) launch_gemm_nt_tc(dA.p, lda, M, dB.p, ldb, N, K, dC.p, N, nullptr, nullptr, real_t(0), nullptr);
+        cudaEventRecord(e1, nullptr);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms_per_launch) *ms_per_launch = ms / repeats;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    if (cudaMemcpy(C, dC.p, (size_t)M * N * sizeof(real_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return 0;
 }
 
 bool get_has_openmp(void)

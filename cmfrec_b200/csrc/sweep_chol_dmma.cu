@@ -249,10 +249,13 @@ __device__ __forceinline__ void dm_c_to_a(double c0, double c1, int lane, double
 }
 
 constexpr int DM_FW = 4;            // warps (= matrices in flight) per block of the factor kernel
+#ifndef DM_FMINB
+#define DM_FMINB 4                  // factor blocks per SM the register allocation aims at
+#endif
 constexpr int DM_SCR = 160;         // doubles of shared scratch per warp
 
 template <int NTR, int MODEL>
-__global__ void __launch_bounds__(DM_FW * 32)
+__global__ void __launch_bounds__(DM_FW * 32, DM_FMINB)
 chol_dmma_factor_kernel(const CgSweepParams p, int kd, int slot0, int nslots, double *ws)
 {
     typedef DmCfg<NTR> Cfg;
@@ -475,7 +478,7 @@ template <int NTR, int MODEL, int BPS> int launch_dmma(const CgSweepParams &p, i
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build, Cfg::NT, smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, factor, DM_FW * 32, 0);
     if (occ < 1 || occf < 1) return 3;
-    const int fcap = dmma_env("CMFB200_DMMA_FBLOCKS", 4);   // factor blocks per SM: bounds the tiles in flight to what L2 holds
+    const int fcap = dmma_env("CMFB200_DMMA_FBLOCKS", 8);   // factor blocks per SM: bounds the tiles in flight to what L2 holds
     if (occf > fcap) occf = fcap;
     const int n = p.plan.n_rows;
     if (n < 1) return 0;

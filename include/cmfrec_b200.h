@@ -139,6 +139,58 @@ int_t topN(
     int_t *outp_ix, real_t *outp_score,
     int_t n_top, int_t n, int nthreads);
 
+/* replaces predict_multiple, reference src/cmfrec.h (body src/common.c:5066-5112): one dot product + biases + mean per
+ * (row, column) pair, NaN where an id is outside [0, m) x [0, n); m == 0 / n == 0: ids are trusted */
+int_t predict_multiple(
+    real_t *A, int_t k_user,
+    real_t *B, int_t k_item,
+    real_t *biasA, real_t *biasB,
+    real_t glob_mean,
+    int_t k, int_t k_main,
+    int_t m, int_t n,
+    int_t predA[], int_t predB[], size_t nnz,
+    real_t *outp,
+    int nthreads);
+
+/* replaces predict_X_old_collective_explicit / _implicit, reference src/cmfrec.h:2192-2210 (src/collective.c:11797-11862) */
+int_t predict_X_old_collective_explicit(
+    int_t row[], int_t col[], real_t *predicted, size_t n_predict,
+    real_t *A, real_t *biasA,
+    real_t *B, real_t *biasB,
+    real_t glob_mean,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    int_t m, int_t n_max,
+    int nthreads);
+int_t predict_X_old_collective_implicit(
+    int_t row[], int_t col[], real_t *predicted, size_t n_predict,
+    real_t *A,
+    real_t *B,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    int_t m, int_t n,
+    int nthreads);
+
+/* replaces topN_old_collective_explicit / _implicit, reference src/cmfrec.h:2104-2127 (src/collective.c:11546-11614) */
+int_t topN_old_collective_explicit(
+    real_t *a_vec, real_t a_bias,
+    real_t *A, real_t *biasA, int_t row_index,
+    real_t *B,
+    real_t *biasB,
+    real_t glob_mean,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    int_t *include_ix, int_t n_include,
+    int_t *exclude_ix, int_t n_exclude,
+    int_t *outp_ix, real_t *outp_score,
+    int_t n_top, int_t n, int_t n_max, bool include_all_X, int nthreads);
+int_t topN_old_collective_implicit(
+    real_t *a_vec,
+    real_t *A, int_t row_index,
+    real_t *B,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    int_t *include_ix, int_t n_include,
+    int_t *exclude_ix, int_t n_exclude,
+    int_t *outp_ix, real_t *outp_score,
+    int_t n_top, int_t n, int nthreads);
+
 /* replaces get_has_openmp, reference src/cmfrec.h:646 (helpers.c:1817) */
 bool get_has_openmp(void);
 
@@ -180,6 +232,22 @@ int cmfb200_gram(const real_t *G, int_t rows, int kk, real_t *gram, int repeats,
 /* Device buffers are recycled between calls through the device's default memory pool (CMFB200_POOL=0 disables it);
  * this hands the cached memory back to the driver. */
 void cmfb200_trim_pool(void);
+
+/* Batched serving from factors kept in HBM (serve.cu).  A [m x (k_user+k+k_main)], B [n x (k_item+k+k_main)] row-major as the
+ * fit entry points return them; biases may be NULL.  cmfb200_serve_predict = predict_multiple for many pairs;
+ * cmfb200_serve_topn = topN for MANY users in one call: scores of the listed users against all items on the tensor cores
+ * (fp32) / DFMA (fp64), the users' seen items (CSR over the listed users: seen_ptr [n_users + 1], seen_idx; NULL = none)
+ * excluded, then an exact per-user radix select; out_ix [n_users x n_top], out_score likewise or NULL; n_top <= 2048.
+ * Equal scores rank the lower item id first.  ms_device (optional): device time of the call. */
+void *cmfb200_serve_create(const real_t *A, int_t m, int_t k_user, const real_t *B, int_t n, int_t k_item, const real_t *biasA,
+                           const real_t *biasB, real_t glob_mean, int_t k, int_t k_main, int *rc_out);
+void cmfb200_serve_destroy(void *h);
+int cmfb200_serve_predict(void *h, const int_t *row, const int_t *col, size_t n_predict, real_t *out);
+int cmfb200_serve_topn(void *h, const int_t *users, int_t n_users, const size_t *seen_ptr, const int_t *seen_idx, int_t n_top,
+                       int_t *out_ix, real_t *out_score, float *ms_device);
+/* C[M x N] = A[M x K] B[N x K]^T on the tcgen05 tensor cores with the 3xTF32 split (gemm_tc.cu; fp32 library, returns 3 in the
+ * fp64 one); host buffers; repeats > 0 also times the launch */
+int cmfb200_gemm_nt(const real_t *A, int lda, int M, const real_t *B, int ldb, int N, int K, real_t *C, int repeats, float *ms_per_launch);
 /* Test aid: fills the shared memory of every SM with `pattern` (e.g. 0x7fc00000 = NaN), so that a kernel launched next
  * that reads shared memory it never wrote produces visibly wrong results instead of depending on what ran before. */
 int cmfb200_debug_poison_smem(unsigned pattern);

@@ -22,7 +22,8 @@ import sys
 import textwrap
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REPLACED = ["fit_collective_explicit_als", "fit_collective_implicit_als", "fit_most_popular", "topN"]
+REPLACED = ["fit_collective_explicit_als", "fit_collective_implicit_als", "fit_most_popular", "topN", "predict_multiple",
+            "predict_X_old_collective_explicit"]
 
 SETUP = '''
 import numpy as np
