@@ -109,7 +109,9 @@ def als_options_type(real):
 
 REFERENCE_ENTRY_POINTS = ("fit_collective_explicit_als", "fit_collective_implicit_als", "fit_most_popular", "topN",
                           "get_has_openmp", "predict_multiple", "predict_X_old_collective_explicit",
-                          "predict_X_old_collective_implicit", "topN_old_collective_explicit", "topN_old_collective_implicit")
+                          "predict_X_old_collective_implicit", "topN_old_collective_explicit", "topN_old_collective_implicit",
+                          "factors_collective_explicit_multiple", "factors_collective_implicit_multiple",
+                          "precompute_collective_explicit", "precompute_collective_implicit")
 
 PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
     "cmfb200_real_name", "cmfb200_device_count", "cmfb200_random_init", "cmfb200_coo_to_csr_and_csc",
@@ -147,6 +149,29 @@ def bind_reference_names(lib, dtype):
     lib.topN_old_collective_explicit.restype = c_int
     lib.topN_old_collective_implicit.argtypes = [P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int]
     lib.topN_old_collective_implicit.restype = c_int
+    lib.factors_collective_explicit_multiple.argtypes = [
+        P, P, c_int, P, c_int, c_int, c_bool, c_bool, c_bool,        # A biasA m U m_u p NA_as_zero_U NA_as_zero_X nonneg
+        P, P, P, c_size_t, P, P, P,                                  # U_row U_col U_sp nnz_U U_csr_p U_csr_i U_csr
+        P, c_int, c_int, P, P, real, P, P,                           # Ub m_ubin pbin C Cb glob_mean biasB U_colmeans
+        P, P, P, c_size_t, P, P, P, P, c_int, P, P,                  # X ixA ixB nnz Xcsr_p Xcsr_i Xcsr Xfull n weight B
+        P, c_bool, c_int, c_int, c_int, c_int,                       # Bi add_implicit_features k k_user k_item k_main
+        real, P, real, P, c_bool, c_bool, c_bool, real,              # lam lam_unique l1_lam l1_lam_unique scale_lam scale_lam_sideinfo scale_bias_const scaling_biasA
+        real, real, real, c_int, c_bool,                             # w_main w_user w_implicit n_max include_all_X
+        P, P, P, P, P, P, P, P, P, c_int]                            # BtB TransBtBinvBt BtXbias BeTBeChol BiTBi TransCtCinvCt CtCw CtUbias B_plus_bias nthreads
+    lib.factors_collective_explicit_multiple.restype = c_int
+    lib.factors_collective_implicit_multiple.argtypes = [
+        P, c_int, P, c_int, c_int, c_bool, c_bool, P, P, P, c_size_t, P, P, P,   # A m U m_u p NA_as_zero_U nonneg U_row U_col U_sp nnz_U U_csr_*
+        P, P, P, c_size_t, P, P, P, P, c_int, P, P,                               # X ixA ixB nnz Xcsr_p Xcsr_i Xcsr B n C U_colmeans
+        c_int, c_int, c_int, c_int, real, real, real, real, real, real, c_bool,   # k k_user k_item k_main lam l1_lam alpha w_main w_user w_main_multiplier apply_log_transf
+        P, P, P, P, c_int]                                                        # BeTBe BtB BeTBeChol CtUbias nthreads
+    lib.factors_collective_implicit_multiple.restype = c_int
+    lib.precompute_collective_explicit.argtypes = [
+        P, c_int, c_int, c_bool, P, c_int, P, c_bool, P, real, c_bool, P, c_bool, c_int, c_int, c_int, c_int, c_bool, c_bool,
+        real, P, c_bool, c_bool, c_bool, real, real, real, real, P, P, P, P, P, P, P, P, P]
+    lib.precompute_collective_explicit.restype = c_int
+    lib.precompute_collective_implicit.argtypes = [P, c_int, P, c_int, P, c_bool, c_int, c_int, c_int, c_int, real, real, real, real,
+                                                   c_bool, c_bool, P, P, P, P]
+    lib.precompute_collective_implicit.restype = c_int
     return lib
 
 

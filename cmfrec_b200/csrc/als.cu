@@ -514,7 +514,8 @@ int AlsState::half_sweep(int which, int iter, int solver)
     p.lam = solveA ? cfg.lam_A : cfg.lam_B;
     p.lam_last = solveA ? cfg.lam_biasA : cfg.lam_biasB;
     p.scale_lam = cfg.scale_lam;
-    p.scale_bias_const = false;
+    p.scale_bias_const = cfg.scale_bias_const;
+    p.last_coord_special = solveA && cfg.last_coord_special;
     p.max_cg_steps = cfg.max_cg_steps;
     const bool both = cfg.user_bias && cfg.item_bias;
     if (cfg.implicit) {

@@ -105,6 +105,8 @@ struct AlsConfig {
     real_t lam_A = 0, lam_B = 0;          // regulariser of the factor columns
     real_t lam_biasA = 0, lam_biasB = 0;  // regulariser of the bias coordinate
     bool scale_lam = false;
+    bool scale_bias_const = false;        // the bias regulariser is NOT multiplied by the row's entry count (fold-in of new rows)
+    bool last_coord_special = false;      // see CgSweepParams::last_coord_special (fold-in of new rows without a user bias)
     int max_cg_steps = 3;
     int rank = 0, world = 1;
 };

@@ -12,6 +12,8 @@
 #include "popular.h"
 #include "topn.h"
 #include "serve.h"
+#include "foldin.h"
+#include "postfit.h"
 #include "gemm_tc.h"
 #include <cmath>
 
@@ -141,6 +143,102 @@ int topN_old_collective_implicit(real_t *a_vec, real_t *A, int_t row_index, real
 {
     return topN_old_collective_explicit(a_vec, real_t(0), A, nullptr, row_index, B, nullptr, real_t(0), k, k_user, k_item, k_main, include_ix,
                                         n_include, exclude_ix, n_exclude, outp_ix, outp_score, n_top, n, n, false, nthreads);
+}
+
+// reference src/collective.c:10865-11174.  Covered on the GPU: sparse X (COO or CSR) of new rows, no side information
+int factors_collective_explicit_multiple(
+    real_t *A, real_t *biasA, int_t m, real_t *U, int_t m_u, int_t p, bool NA_as_zero_U, bool NA_as_zero_X, bool nonneg,
+    int_t U_row[], int_t U_col[], real_t *U_sp, size_t nnz_U, size_t U_csr_p[], int_t U_csr_i[], real_t *U_csr, real_t *Ub,
+    int_t m_ubin, int_t pbin, real_t *C, real_t *Cb, real_t glob_mean, real_t *biasB, real_t *U_colmeans, real_t *X, int_t ixA[],
+    int_t ixB[], size_t nnz, size_t *Xcsr_p, int_t *Xcsr_i, real_t *Xcsr, real_t *Xfull, int_t n, real_t *weight, real_t *B,
+    real_t *Bi, bool add_implicit_features, int_t k, int_t k_user, int_t k_item, int_t k_main, real_t lam, real_t *lam_unique,
+    real_t l1_lam, real_t *l1_lam_unique, bool scale_lam, bool scale_lam_sideinfo, bool scale_bias_const, real_t scaling_biasA,
+    real_t w_main, real_t w_user, real_t w_implicit, int_t n_max, bool include_all_X, real_t *BtB, real_t *TransBtBinvBt,
+    real_t *BtXbias, real_t *BeTBeChol, real_t *BiTBi, real_t *TransCtCinvCt, real_t *CtCw, real_t *CtUbias, real_t *B_plus_bias,
+    int nthreads)
+{
+    (void)m_u; (void)p; (void)m_ubin; (void)pbin; (void)C; (void)Cb; (void)U_colmeans; (void)Bi; (void)w_user; (void)w_implicit;
+    (void)BtB; (void)TransBtBinvBt; (void)BtXbias; (void)BeTBeChol; (void)BiTBi; (void)TransCtCinvCt; (void)CtCw; (void)CtUbias;
+    (void)B_plus_bias; (void)nthreads; (void)U_row; (void)U_col; (void)U_csr_i;
+    if (U || U_sp || U_csr_p || U_csr || nnz_U || Ub) return foldin_refuse("side information for new rows");
+    if (NA_as_zero_U || NA_as_zero_X) return foldin_refuse("NA_as_zero for new rows");
+    if (Xfull) return foldin_refuse("dense X for new rows");
+    if (weight) return foldin_refuse("observation weights for new rows");
+    if (add_implicit_features) return foldin_refuse("implicit features for new rows");
+    if (nonneg || l1_lam != 0 || l1_lam_unique) return foldin_refuse("non-negativity / L1 for new rows");
+    if (k_user || k_item) return foldin_refuse("k_user / k_item for new rows");
+    FoldinExplicitArgs a{A, biasA, m, ixA, ixB, X, nnz, Xcsr_p, Xcsr_i, Xcsr, B, biasB, n, n_max, include_all_X, glob_mean, k, k_main,
+                         lam, lam_unique, scale_lam, scale_lam_sideinfo, scale_bias_const, scaling_biasA, w_main};
+    return foldin_explicit(a);
+}
+
+// reference src/collective.c:11176-11330
+int factors_collective_implicit_multiple(
+    real_t *A, int_t m, real_t *U, int_t m_u, int_t p, bool NA_as_zero_U, bool nonneg, int_t U_row[], int_t U_col[], real_t *U_sp,
+    size_t nnz_U, size_t U_csr_p[], int_t U_csr_i[], real_t *U_csr, real_t *X, int_t ixA[], int_t ixB[], size_t nnz, size_t *Xcsr_p,
+    int_t *Xcsr_i, real_t *Xcsr, real_t *B, int_t n, real_t *C, real_t *U_colmeans, int_t k, int_t k_user, int_t k_item, int_t k_main,
+    real_t lam, real_t l1_lam, real_t alpha, real_t w_main, real_t w_user, real_t w_main_multiplier, bool apply_log_transf,
+    real_t *BeTBe, real_t *BtB, real_t *BeTBeChol, real_t *CtUbias, int nthreads)
+{
+    (void)m_u; (void)p; (void)C; (void)U_colmeans; (void)w_user; (void)BeTBe; (void)BtB; (void)BeTBeChol; (void)CtUbias; (void)nthreads;
+    (void)U_row; (void)U_col; (void)U_csr_i;
+    if (U || U_sp || U_csr_p || U_csr || nnz_U) return foldin_refuse("side information for new rows");
+    if (NA_as_zero_U) return foldin_refuse("NA_as_zero for new rows");
+    if (nonneg || l1_lam != 0) return foldin_refuse("non-negativity / L1 for new rows");
+    if (k_user || k_item) return foldin_refuse("k_user / k_item for new rows");
+    FoldinImplicitArgs a{A, m, ixA, ixB, X, nnz, Xcsr_p, Xcsr_i, Xcsr, B, n, k, k_main, lam, alpha, w_main, w_main_multiplier, apply_log_transf};
+    return foldin_implicit(a);
+}
+
+// reference src/collective.c:10209-10485: the matrices kept for predictions on new rows
+int precompute_collective_explicit(
+    real_t *B, int_t n, int_t n_max, bool include_all_X, real_t *C, int_t p, real_t *Bi, bool add_implicit_features, real_t *biasB,
+    real_t glob_mean, bool NA_as_zero_X, real_t *U_colmeans, bool NA_as_zero_U, int_t k, int_t k_user, int_t k_item, int_t k_main,
+    bool user_bias, bool nonneg, real_t lam, real_t *lam_unique, bool scale_lam, bool scale_lam_sideinfo, bool scale_bias_const,
+    real_t scaling_biasA, real_t w_main, real_t w_user, real_t w_implicit, real_t *B_plus_bias, real_t *BtB, real_t *TransBtBinvBt,
+    real_t *BtXbias, real_t *BeTBeChol, real_t *BiTBi, real_t *TransCtCinvCt, real_t *CtCw, real_t *CtUbias)
+{
+    (void)glob_mean; (void)U_colmeans; (void)scaling_biasA; (void)BtXbias; (void)CtUbias; (void)nonneg;
+    if (NA_as_zero_X || NA_as_zero_U) return foldin_refuse("NA_as_zero in precompute_collective_explicit");
+    if (k_user || k_item) return foldin_refuse("k_user / k_item in precompute_collective_explicit");
+    if ((scale_lam || scale_lam_sideinfo) && scale_bias_const && user_bias) return foldin_refuse("scale_bias_const");
+    if ((C || add_implicit_features) && k_main) return foldin_refuse("k_main together with side information / implicit features");
+    if (!B || n < 1) return 2;
+    if (n_max == 0) n_max = n;
+    if (include_all_X) n = n_max;
+    real_t lam_main = lam_unique ? lam_unique[2] : lam, lam_bias = lam_unique ? lam_unique[user_bias ? 0 : 2] : lam;
+    if (w_main != 1) {
+        lam_main /= w_main; lam_bias /= w_main; w_user /= w_main; w_implicit /= w_main;
+    }
+    PostfitExplicit pf;
+    pf.B = B; pf.biasB = biasB; pf.n = n; pf.kk = k + k_main;
+    pf.user_bias = user_bias; pf.item_bias = biasB != nullptr;
+    pf.lam = lam_main; pf.lam_bias = lam_bias; pf.scale_lam = scale_lam || scale_lam_sideinfo;
+    pf.B_plus_bias = B_plus_bias; pf.BtB = BtB; pf.TransBtBinvBt = TransBtBinvBt;
+    if (C || add_implicit_features) {
+        pf.C = C; pf.p = C ? p : 0; pf.w_user = w_user;
+        pf.Bi = add_implicit_features ? Bi : nullptr; pf.implicit_features = add_implicit_features; pf.w_implicit = w_implicit;
+        pf.scale_lam_sideinfo = scale_lam_sideinfo;
+        pf.BiTBi = BiTBi; pf.TransCtCinvCt = TransCtCinvCt; pf.CtCw = CtCw; pf.BeTBeChol = BeTBeChol;
+    }
+    return postfit_explicit(pf);
+}
+
+// reference src/collective.c:10487-10573
+int precompute_collective_implicit(real_t *B, int_t n, real_t *C, int_t p, real_t *U_colmeans, bool NA_as_zero_U, int_t k, int_t k_user,
+                                   int_t k_item, int_t k_main, real_t lam, real_t w_main, real_t w_user, real_t w_main_multiplier,
+                                   bool nonneg, bool extra_precision, real_t *BtB, real_t *BeTBe, real_t *BeTBeChol, real_t *CtUbias)
+{
+    (void)U_colmeans; (void)nonneg; (void)extra_precision; (void)CtUbias;
+    if (NA_as_zero_U) return foldin_refuse("NA_as_zero_U in precompute_collective_implicit");
+    if (k_user || k_item) return foldin_refuse("k_user / k_item in precompute_collective_implicit");
+    if (!B || n < 1 || !BtB) return 2;
+    if (w_main_multiplier != 1) w_main *= w_main_multiplier;
+    if (w_main != 1) {
+        lam /= w_main;
+        w_user /= w_main;
+    }
+    return postfit_implicit(B, n, k + k_main, lam, BtB, p ? C : nullptr, p, w_user, BeTBe, BeTBeChol, false);
 }
 
 // ---- batched serving from factors resident in HBM (serve.cu)

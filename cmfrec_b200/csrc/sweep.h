@@ -38,6 +38,8 @@ struct CgSweepParams {
     bool solve_bias;              // the solved row has a bias coordinate (Fbias; its opposing value is 1)
     bool center_opp;              // subtract the opposing row's bias (Gbias) from every x before use
     bool bias_start_one;          // start the bias coordinate from 1.0 instead of the stored bias
+    bool last_coord_special;      // exact solves only: the LAST coordinate is regularised by lam_last even without a bias
+                                  // (the reference's fold-in without user bias, src/collective.c:3780-3796 -> common.c:718-721)
     int max_cg_steps;
     const real_t *gram;           // constant [kk x kk] matrix (row-major, full symmetric) added to every row's system:
                                   // implicit model: G^T G; explicit model with side info / implicit features: Q

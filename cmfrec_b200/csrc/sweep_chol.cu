@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(NT) chol_sweep_kernel(const CgSweepParams p, i
                         if (a < kd && b < kd) {
                             T v = acc[s][i][j];
                             if (MODEL != kModelExplicit && p.gram && a < kk && b < kk) v += p.gram[(size_t)a * kk + b];
-                            if (a == b) v += (hb && a == kd - 1) ? lam_last : lam;
+                            if (a == b) v += ((hb || p.last_coord_special) && a == kd - 1) ? lam_last : lam;
                             if (a <= b) {
                                 M[b * kdp + a] = v;   // lower triangle is what the factorisation uses
                                 if (my_ti[s] != my_tj[s] || a != b) M[a * kdp + b] = v;
@@ -348,7 +348,7 @@ static bool dmma_enabled()
 
 int launch_explicit_chol_sweep(const CgSweepParams &p, cudaStream_t stream)
 {
-    if (nm_enabled()) {
+    if (nm_enabled() && !p.last_coord_special) {
         const int rc = launch_explicit_chol_sweep_nm(p, stream);
         if (rc != 3) return rc;
     }

@@ -218,7 +218,7 @@ chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nslots, dou
                     if (a < kd && b < kd) {
                         double v = acc[s][e];
                         if (MODEL != kModelExplicit && p.gram && a < kk && b < kk) v += __ldg(p.gram + (size_t)a * kk + b);
-                        if (a == b) v += (hb && a == kd - 1) ? lam_last : lam;
+                        if (a == b) v += ((hb || p.last_coord_special) && a == kd - 1) ? lam_last : lam;
                         acc[s][e] = v;
                     } else if (MODEL != kModelExplicit && a == kd && b < kk && p.qvec) {
                         acc[s][e] += __ldg(p.qvec + (size_t)row * (size_t)p.ldq + b);

@@ -191,6 +191,105 @@ int_t topN_old_collective_implicit(
     int_t *outp_ix, real_t *outp_score,
     int_t n_top, int_t n, int nthreads);
 
+/* replaces factors_collective_explicit_multiple, reference src/cmfrec.h:2012-2047 (body src/collective.c:10865-11174): factors
+ * (and biases) of NEW rows given the fitted item factors.  GPU path: sparse X of the new rows (COO or CSR) without side
+ * information -- the exact (Cholesky) half-sweep of the fit with B fixed; any other argument combination returns 2. */
+int_t factors_collective_explicit_multiple(
+    real_t *A, real_t *biasA, int_t m,
+    real_t *U, int_t m_u, int_t p,
+    bool NA_as_zero_U, bool NA_as_zero_X,
+    bool nonneg,
+    int_t U_row[], int_t U_col[], real_t *U_sp, size_t nnz_U,
+    size_t U_csr_p[], int_t U_csr_i[], real_t *U_csr,
+    real_t *Ub, int_t m_ubin, int_t pbin,
+    real_t *C, real_t *Cb,
+    real_t glob_mean, real_t *biasB,
+    real_t *U_colmeans,
+    real_t *X, int_t ixA[], int_t ixB[], size_t nnz,
+    size_t *Xcsr_p, int_t *Xcsr_i, real_t *Xcsr,
+    real_t *Xfull, int_t n,
+    real_t *weight,
+    real_t *B,
+    real_t *Bi, bool add_implicit_features,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    real_t lam, real_t *lam_unique,
+    real_t l1_lam, real_t *l1_lam_unique,
+    bool scale_lam, bool scale_lam_sideinfo,
+    bool scale_bias_const, real_t scaling_biasA,
+    real_t w_main, real_t w_user, real_t w_implicit,
+    int_t n_max, bool include_all_X,
+    real_t *BtB,
+    real_t *TransBtBinvBt,
+    real_t *BtXbias,
+    real_t *BeTBeChol,
+    real_t *BiTBi,
+    real_t *TransCtCinvCt,
+    real_t *CtCw,
+    real_t *CtUbias,
+    real_t *B_plus_bias,
+    int nthreads);
+
+/* replaces factors_collective_implicit_multiple, reference src/cmfrec.h:2048-2070 (body src/collective.c:11176-11330) */
+int_t factors_collective_implicit_multiple(
+    real_t *A, int_t m,
+    real_t *U, int_t m_u, int_t p,
+    bool NA_as_zero_U,
+    bool nonneg,
+    int_t U_row[], int_t U_col[], real_t *U_sp, size_t nnz_U,
+    size_t U_csr_p[], int_t U_csr_i[], real_t *U_csr,
+    real_t *X, int_t ixA[], int_t ixB[], size_t nnz,
+    size_t *Xcsr_p, int_t *Xcsr_i, real_t *Xcsr,
+    real_t *B, int_t n,
+    real_t *C,
+    real_t *U_colmeans,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    real_t lam, real_t l1_lam, real_t alpha, real_t w_main, real_t w_user,
+    real_t w_main_multiplier,
+    bool apply_log_transf,
+    real_t *BeTBe,
+    real_t *BtB,
+    real_t *BeTBeChol,
+    real_t *CtUbias,
+    int nthreads);
+
+/* replaces precompute_collective_explicit, reference src/cmfrec.h:1922-1945 (body src/collective.c:10209-10485) */
+int_t precompute_collective_explicit(
+    real_t *B, int_t n, int_t n_max, bool include_all_X,
+    real_t *C, int_t p,
+    real_t *Bi, bool add_implicit_features,
+    real_t *biasB, real_t glob_mean, bool NA_as_zero_X,
+    real_t *U_colmeans, bool NA_as_zero_U,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    bool user_bias,
+    bool nonneg,
+    real_t lam, real_t *lam_unique,
+    bool scale_lam, bool scale_lam_sideinfo,
+    bool scale_bias_const, real_t scaling_biasA,
+    real_t w_main, real_t w_user, real_t w_implicit,
+    real_t *B_plus_bias,
+    real_t *BtB,
+    real_t *TransBtBinvBt,
+    real_t *BtXbias,
+    real_t *BeTBeChol,
+    real_t *BiTBi,
+    real_t *TransCtCinvCt,
+    real_t *CtCw,
+    real_t *CtUbias);
+
+/* replaces precompute_collective_implicit, reference src/cmfrec.h:1946-1958 (body src/collective.c:10487-10573) */
+int_t precompute_collective_implicit(
+    real_t *B, int_t n,
+    real_t *C, int_t p,
+    real_t *U_colmeans, bool NA_as_zero_U,
+    int_t k, int_t k_user, int_t k_item, int_t k_main,
+    real_t lam, real_t w_main, real_t w_user, real_t w_main_multiplier,
+    bool nonneg,
+    bool extra_precision,
+    real_t *BtB,
+    real_t *BeTBe,
+    real_t *BeTBeChol,
+    real_t *CtUbias);
+
 /* replaces get_has_openmp, reference src/cmfrec.h:646 (helpers.c:1817) */
 bool get_has_openmp(void);
 
