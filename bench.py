@@ -319,7 +319,7 @@ def main():
     assert rc == 0, "cmfb200_als_create -> %d" % rc
     assert L.cmfb200_als_set_factors(hnd, ptr(A0), ptr(bA), ptr(B0), ptr(bB)) == 0
     if w.get("side") or w.get("implicit_features"):
-        assert world == 1, "side information / implicit features are single-GPU in this round"
+        assert world == 1 or not w.get("side"), "dense side information is single-GPU; implicit features shard like A / B"
         U, I = side_info(w, m, n, dt)
         if U is not None:
             U = (U - U.mean(axis=0, dtype=dt)).astype(dt); I = (I - I.mean(axis=0, dtype=dt)).astype(dt)
@@ -431,7 +431,7 @@ def main():
             # every rank passes the full COO triplets from pinned host memory and receives the full factors; ingestion
             # (CSR / CSC, centring, biases), the dealing of the rows to the ranks, K iterations with their all-gathers and
             # the download are all inside the timed region
-            assert not (w.get("side") or w.get("implicit_features"))
+            assert not w.get("side")
             pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()
             pa, pb, px = pin(a), pin(b), pin(x)
             outbuf = dict(A=pin(np.zeros((m, w["k"]), dt)), B=pin(np.zeros((n, w["k"]), dt)))
@@ -441,9 +441,10 @@ def main():
                                                copy_inputs=False, out=outbuf)
             else:
                 outbuf.update(biasA=pin(np.zeros(m, dt)), biasB=pin(np.zeros(n, dt)))
+                extra = dict(add_implicit_features=bool(w.get("implicit_features")), w_implicit=w.get("w_implicit", 1.0))
                 run = lambda nit: fit_explicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
                                                niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
-                                               copy_inputs=False, out=outbuf)
+                                               copy_inputs=False, out=outbuf, **extra)
             fresh_nccl_id()
             assert L.cmfb200_set_world(rank, world, opt.nccl_id) == 0
             assert run(1)["rc"] == 0

@@ -497,6 +497,12 @@ int AlsState::download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, 
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
+int AlsState::download_matrix(int which, const real_t *src, int ld, real_t *h, int ldh)
+{
+    if (download_rows(src, ld, which ? cfg.m : cfg.n, cfg.kk, which ? renA : renB, h, ldh, stream)) return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
 int AlsState::half_sweep(int which, int iter, int solver)
 {
     const bool solveA = which == 1;

@@ -174,6 +174,8 @@ public:
     int upload_coordinates(const real_t *hA, const real_t *hB);   // keeps the bias slots already on the device
     int upload_bias(int which, const real_t *hbias);
     int download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB);
+    // any device matrix with one row per user (which = 1) / item (0) in device numbering -> host, caller numbering, kk columns
+    int download_matrix(int which, const real_t *src, int ld, real_t *h, int ldh);
     // which: 0 = update B (items) from A, 1 = update A (users) from B.  `solver`: 0 = CG, 1 = Cholesky
     int half_sweep(int which, int iter, int solver);
     int exchange(int which);      // all-gather the freshly solved block (no-op on one GPU)

@@ -420,7 +420,8 @@ int cmfb200_als_attach_collective(cmfb200_als *s, const real_t *U_centred, int p
                                   int add_implicit_features, real_t w_user, real_t w_item, real_t w_implicit, real_t lam_C,
                                   real_t lam_D, real_t lam_Bi, real_t lam_Ai)
 {
-    if (!s || s->st.cfg.implicit || s->st.cfg.world != 1 || s->st.coll) return 2;
+    if (!s || s->st.cfg.implicit || s->st.coll) return 2;
+    if (s->st.cfg.world != 1 && (U_centred || I_centred)) return 2;   // sharded: implicit features only (collective.cu)
     CollectiveConfig cc;
     cc.p = U_centred ? p : 0;
     cc.q = I_centred ? q : 0;

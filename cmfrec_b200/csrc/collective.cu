@@ -11,6 +11,7 @@
 #include "collective.h"
 #include "dense_small.h"
 #include "postfit.h"
+#include "nccl_link.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,10 @@ int CollectiveState::setup(AlsState *state, const CollectiveConfig &c, const rea
     const int_t m = st->cfg.m, n = st->cfg.n;
     cudaStream_t s = st->stream;
     const int ldq = cmf_ld_for(k);
+    // more than one GPU: implicit features only (Ai / Bi are replicated like A / B, device numbering, every rank solves
+    // its own block of rows and the blocks are all-gathered); dense side information is not sharded yet
+    if (st->cfg.world > 1 && (cc.p > 0 || cc.q > 0)) return 2;
+    const size_t mp = (size_t)st->renA.rows_padded, np_ = (size_t)st->renB.rows_padded;
     if (cc.p > 0) {
         if (!Uc.alloc((size_t)m * cc.p) || !C.alloc((size_t)cc.p * k)) return 1;
         cudaMemcpyAsync(Uc.p, Uc_host, Uc.n * sizeof(real_t), cudaMemcpyHostToDevice, s);
@@ -37,14 +42,14 @@ int CollectiveState::setup(AlsState *state, const CollectiveConfig &c, const rea
         cudaMemsetAsync(D.p, 0, D.n * sizeof(real_t), s);
     }
     if (cc.implicit_features) {
-        if (!Ai.alloc((size_t)m * k) || !Bi.alloc((size_t)n * k)) return 1;
+        if (!Ai.alloc(mp * k) || !Bi.alloc(np_ * k)) return 1;
         cudaMemsetAsync(Ai.p, 0, Ai.n * sizeof(real_t), s);
         cudaMemsetAsync(Bi.p, 0, Bi.n * sizeof(real_t), s);
     }
     const int pmax = std::max(std::max(cc.p, cc.q), k);
     if (!QA.alloc((size_t)k * k) || !QB.alloc((size_t)k * k) || !G1.alloc((size_t)k * k) || !G2.alloc((size_t)k * k) ||
         !T1.alloc((size_t)pmax * k) || !Ldev.alloc((size_t)k * k) || !ws.alloc(xty_workspace_elems(pmax, k)) ||
-        !qA.alloc((size_t)m * ldq) || !qB.alloc((size_t)n * ldq))
+        !qA.alloc(mp * ldq) || !qB.alloc(np_ * ldq))
         return 1;
     st->extra_ldq[0] = st->extra_ldq[1] = ldq;
     return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 1;
@@ -74,8 +79,13 @@ int CollectiveState::update_implicit_factor(const DeviceSide &side, const real_t
     if (rc) return rc;
     if ((rc = launch_spd_factor(G1.p, k, lam, Ldev.p, s))) return rc;
     if ((rc = launch_spmm_ones(side.view(), side.plan(), F, ldF, k, real_t(1), false, Out, k, s))) return rc;
-    if ((rc = launch_tri_solve_rows(Ldev.p, k, Out, k, side.n_order, s))) return rc;
+    // this rank's rows are the contiguous block [row_begin, row_begin + n_order) of the device numbering (all rows on one GPU)
+    if ((rc = launch_tri_solve_rows(Ldev.p, k, Out + (size_t)side.row_begin * k, k, side.n_order, s))) return rc;
     st->launches += 5;
+    if (st->link) {
+        if ((rc = st->link->all_gather_inplace(Out, (size_t)side.block * k * sizeof(real_t), s))) return rc;
+        st->launches += 1;
+    }
     return 0;
 }
 
@@ -141,23 +151,25 @@ int CollectiveState::iteration(int it, int solver)
     if (cc.implicit_features) {
         if (stop_flag()) return 3;
         say("Updating Bi...");
-        if ((rc = update_implicit_factor(st->byB, st->A.p, st->ldA, m, cc.lam_Bi, Bi.p))) return rc;
+        if ((rc = update_implicit_factor(st->byB, st->A.p, st->ldA, st->renA.rows_padded, cc.lam_Bi, Bi.p))) return rc;
         if ((rc = done())) return rc;
         if (stop_flag()) return 3;
         say("Updating Ai...");
-        if ((rc = update_implicit_factor(st->byA, st->B.p, st->ldB, n, cc.lam_Ai, Ai.p))) return rc;
+        if ((rc = update_implicit_factor(st->byA, st->B.p, st->ldB, st->renB.rows_padded, cc.lam_Ai, Ai.p))) return rc;
         if ((rc = done())) return rc;
     }
     // B given A (extras use D and Ai), then A given the new B (extras use C and Bi)
     if (stop_flag()) return 3;
     say("Updating B ...");
-    if ((rc = build_extras(0, st->byB, n, Ic.p, cc.q, D.p, cc.w_item, Ai.p, m))) return rc;
+    if ((rc = build_extras(0, st->byB, n, Ic.p, cc.q, D.p, cc.w_item, Ai.p, st->renA.rows_padded))) return rc;
     if ((rc = st->half_sweep(0, it, solver))) return rc;
+    if ((rc = st->exchange(0))) return rc;
     if ((rc = done())) return rc;
     if (stop_flag()) return 3;
     say("Updating A ...");
-    if ((rc = build_extras(1, st->byA, m, Uc.p, cc.p, C.p, cc.w_user, Bi.p, n))) return rc;
+    if ((rc = build_extras(1, st->byA, m, Uc.p, cc.p, C.p, cc.w_user, Bi.p, st->renB.rows_padded))) return rc;
     if ((rc = st->half_sweep(1, it, solver))) return rc;
+    if ((rc = st->exchange(1))) return rc;
     return done();
 }
 
@@ -175,8 +187,9 @@ int CollectiveState::download(real_t *hC, real_t *hD, real_t *hAi, real_t *hBi)
     cudaStream_t s = st->stream;
     if (hC && C.n) cudaMemcpyAsync(hC, C.p, C.n * sizeof(real_t), cudaMemcpyDeviceToHost, s);
     if (hD && D.n) cudaMemcpyAsync(hD, D.p, D.n * sizeof(real_t), cudaMemcpyDeviceToHost, s);
-    if (hAi && Ai.n) cudaMemcpyAsync(hAi, Ai.p, Ai.n * sizeof(real_t), cudaMemcpyDeviceToHost, s);
-    if (hBi && Bi.n) cudaMemcpyAsync(hBi, Bi.p, Bi.n * sizeof(real_t), cudaMemcpyDeviceToHost, s);
+    const int k = st->cfg.kk;
+    if (hAi && Ai.n && st->download_matrix(1, Ai.p, k, hAi, k)) return 1;   // back to the caller's row numbering
+    if (hBi && Bi.n && st->download_matrix(0, Bi.p, k, hBi, k)) return 1;
     return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 1;
 }
 

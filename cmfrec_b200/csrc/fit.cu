@@ -165,7 +165,7 @@ int fit_explicit(const ExplicitArgs &a)
     const WorldSetting &ws = world_setting();
     cfg.rank = ws.rank;
     cfg.world = ws.world;
-    if (cfg.world > 1 && collective) return refuse("side information / implicit features on more than one GPU");
+    if (cfg.world > 1 && (a.U || a.II)) return refuse("dense side information on more than one GPU");
     BiasInit bi;
     if (has_bias) {
         if (a.user_bias && a.item_bias) bi.which = 3;

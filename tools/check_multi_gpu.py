@@ -68,6 +68,25 @@ for implicit in (False, True):
             keys = ("A", "B") if implicit else ("A", "B", "biasA", "biasB")
             report("fit_collective_%s_als" % ("implicit" if implicit else "explicit"), [a[key] for key in keys], [b[key] for key in keys], implicit, dt)
         dist.barrier()
+# ---- BASELINE config 4 style: explicit feedback with implicit features (Ai, Bi sharded like A, B; collective.cu)
+for dt in (np.dtype(np.float32), np.dtype(np.float64)):
+    L = _lib.load(dt)
+    m, n, k = 5003, 3001, 32
+    ixA, ixB, X = synth_coo(m, n, 200000, dt, seed=6)
+    nid = nccl_id_for_all_ranks(L, rank, world)
+    assert L.cmfb200_set_world(rank, world, C.cast(nid, C.c_void_p)) == 0
+    fit = lambda: fit_explicit(L, dt, ixA, ixB, X, m, n, k, lam=0.05, scale_lam=True, niter=3, finalize_chol=True,
+                               add_implicit_features=True, w_implicit=0.5)
+    a = fit()
+    assert a["rc"] == 0, a["rc"]
+    assert L.cmfb200_set_world(0, 1, None) == 0
+    if rank == 0:
+        b = fit()
+        keys = ("A", "B", "biasA", "biasB", "Ai", "Bi")
+        # the k x k Grams of A / B / Ai / Bi are summed over the replica in DEVICE row order, which depends on the dealing:
+        # rounding-level differences against the 1-GPU fit, like the implicit model's Gram
+        report("fit_collective_explicit_als implicit features", [a[key] for key in keys], [b[key] for key in keys], True, dt)
+    dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
 dist.destroy_process_group()
