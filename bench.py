@@ -64,6 +64,9 @@ WORKLOADS = {
     # BASELINE.json config 4: CG, fp32, k=64, add_implicit_features (w_implicit = 0.5)
     "ml10m_explicit_cg_k64_f32_implicit_features": dict(shape="ml10m", implicit=False, k=64, dtype="f32", use_cg=True,
                                                         implicit_features=True, w_implicit=0.5),
+    # BASELINE.json config 5: CMF_implicit ALS-CG k=256 fp32, 10 M x 1 M, ~1e9 entries, generated ON THE DEVICE;
+    # --scale shrinks m, n (and so nnz) for smaller boxes: 1.0 is the full configuration, meant for 8 GPUs
+    "cfg5_implicit_cg_k256_f32": dict(shape="cfg5", implicit=True, k=256, dtype="f32", use_cg=True, device_generated=True),
 }
 HYPER = dict(explicit=dict(lam=0.05, scale_lam=True, user_bias=True, item_bias=True, center=True, max_cg_steps=3),
              implicit=dict(lam=5.0, alpha=1.0, max_cg_steps=3))
@@ -207,6 +210,148 @@ def time_reference(w, data, steps, warmup, nthreads):
                 sample="full workload, one fit call of %d ALS iterations, nthreads=%d" % (steps, nthreads))
 
 
+def generate_cfg5_on_device(torch, m, n, seed):
+    """COO triplets of BASELINE config 5 on the current CUDA device (every rank generates the same arrays): row degrees
+    lognormal with mean 100, columns Zipf-like (log-uniform ranks, then scattered over the ids by an affine map),
+    values ceil(lognormal(1, 1.5)) -- SURVEY.md 8(d).  Returns int32 rows, int32 cols, float32 values."""
+    import math
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    deg = torch.exp(torch.randn(m, generator=g, device=dev) + (math.log(100.0) - 0.5)).round_().clamp_(1, max(1, n // 2)).to(torch.int64)
+    nnz = int(deg.sum().item())
+    assert nnz < 2 ** 31, "the device-side compression indexes entries with 32 bits"
+    rows = torch.repeat_interleave(torch.arange(m, dtype=torch.int32, device=dev), deg, output_size=nnz)
+    del deg
+    cols = torch.empty(nnz, dtype=torch.int32, device=dev)
+    vals = torch.empty(nnz, dtype=torch.float32, device=dev)
+    step = 1 << 26
+    mult = 2654435761 % n
+    while math.gcd(mult, n) != 1:
+        mult += 1
+    for s in range(0, nnz, step):
+        e = min(nnz, s + step)
+        u = torch.rand(e - s, generator=g, device=dev, dtype=torch.float64)
+        c = torch.exp(u * math.log(n)).to(torch.int64).sub_(1).clamp_(0, n - 1)
+        cols[s:e] = ((c * mult + 12345) % n).to(torch.int32)
+        z = torch.randn(e - s, generator=g, device=dev)
+        vals[s:e] = torch.ceil(torch.exp(1.0 + 1.5 * z)).clamp_(1.0, 1e6)
+        del u, c, z
+    return rows, cols, vals, nnz
+
+
+def run_device_generated(args, w, config, rank, world, local_rank):
+    """Workloads whose data never exists on the host (config 5): generate on the device, build / deal on the device
+    (cmfb200_als_create_from_device_coo), device-side starting factors, timed iterations as in main()."""
+    import torch
+    import torch.distributed as dist
+    from cmfrec_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dt = np.dtype(np.float32)
+    L = _lib.load(dt)
+    if L.cmfb200_device_count() < 1:
+        raise RuntimeError("no CUDA device: cmfrec_b200 has no CPU path")
+    m, n = max(64, int(10_000_000 * args.scale)), max(64, int(1_000_000 * args.scale))
+    t0 = time.perf_counter()
+    rows, cols, vals, nnz = generate_cfg5_on_device(torch, m, n, 20260105)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    h = HYPER["implicit"]
+    config.update(m=m, n=n, nnz=nnz, scale=args.scale, generated="on the device, every rank the same arrays (seed 20260105)")
+    stream = torch.cuda.current_stream().cuda_stream
+    opt = L.AlsOptions()
+    opt.implicit = 1
+    opt.m, opt.n, opt.k = m, n, w["k"]
+    opt.lam_A = opt.lam_B = opt.lam_biasA = opt.lam_biasB = h["lam"]
+    opt.max_cg_steps = h["max_cg_steps"]
+    opt.rank, opt.world = rank, world
+    idbuf = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            assert L.cmfb200_nccl_unique_id(raw) == 0
+            idt = torch.tensor(list(raw), dtype=torch.uint8)
+        idt = idt.cuda()
+        dist.broadcast(idt, 0)
+        idbuf = (C.c_ubyte * 128)(*idt.cpu().tolist())
+        opt.nccl_id = C.cast(idbuf, C.c_void_p)
+    opt.stream = stream
+    hnd = C.c_void_p()
+    t0 = time.perf_counter()
+    rc = L.cmfb200_als_create_from_device_coo(C.byref(hnd), C.byref(opt), C.c_void_p(rows.data_ptr()), C.c_void_p(cols.data_ptr()),
+                                              C.c_void_p(vals.data_ptr()), nnz, 0.0, h["alpha"])
+    assert rc == 0, "cmfb200_als_create_from_device_coo -> %d" % rc
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    del rows, cols, vals
+    torch.cuda.empty_cache()
+    assert L.cmfb200_als_random_factors(hnd, 1, 2.0 ** -7) == 0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ms = C.c_float(0)
+    it = 0
+    for _ in range(max(args.warmup, 3)):
+        assert L.cmfb200_als_timed_iterate(hnd, it, 1, 1 << 30, 1, 0, C.byref(ms)) == 0
+        it += 1
+    L.cmfb200_als_set_profile(hnd, 1)
+    launches0 = L.cmfb200_als_launch_count(hnd)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        assert L.cmfb200_als_timed_iterate(hnd, it, 1, 1 << 30, 1, 0, C.byref(ms)) == 0
+        total_ms += ms.value
+        it += 1
+    barrier()
+    clocks = sampler.stop()
+    launches = L.cmfb200_als_launch_count(hnd) - launches0
+    kt = [C.c_double(0), C.c_double(0)]
+    kc = [C.c_longlong(0), C.c_longlong(0)]
+    for which in (0, 1):
+        L.cmfb200_als_read_profile(hnd, which, C.byref(kt[which]), C.byref(kc[which]))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    bytes_B, bytes_A = algorithmic_bytes(w, m, n, nnz, dt)
+    kernel_ms = kt[0].value + kt[1].value
+    kernel_launches = kc[0].value + kc[1].value
+    bytes_per_launch = (bytes_B + bytes_A) / 2.0 / world
+    avg_ms = kernel_ms / max(kernel_launches, 1)
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    kernel="cg_resident_kernel", avg_launch_ms=avg_ms, launches_timed=int(kernel_launches),
+                    algorithmic_bytes_per_launch=bytes_per_launch, kernel_share_of_step=kernel_ms / total_ms if total_ms else None,
+                    peak_source=peak_src, B_sweep_ms=kt[0].value / max(kc[0].value, 1), A_sweep_ms=kt[1].value / max(kc[1].value, 1))
+    L.cmfb200_als_destroy(hnd)
+    if rank == 0:
+        emit(dict(metric="rows_solved_per_sec", value=(m + n) / (ms_per_step * 1e-3), unit="rows/s", n_gpus=world, steps=args.steps,
+                  warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                  dtype=w["dtype"], data="synthetic", config=config, roofline=roofline, clocks=clocks, gpu_launches=int(launches),
+                  e2e=None, e2e_note="the triplets never exist on the host at this size: generated on the device in %.1f s, "
+                                     "CSR / CSC built and dealt on the device in %.1f s (both outside the timed region)" % (t_gen, t_setup),
+                  cpu_baseline=None, sec_per_iter=ms_per_step * 1e-3))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +361,7 @@ def main():
     ap.add_argument("--workload", default="ml10m_explicit_cg_k64_f32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scale", type=float, default=1.0, help="size factor of the device-generated workload (cfg5)")
     args = ap.parse_args()
     claim_stdout()
     w = WORKLOADS[args.workload]
@@ -250,6 +396,9 @@ def main():
                     gpu_launches=0, sec_per_iter=r["sec_iter"])
         emit(line)
         return
+
+    if w.get("device_generated"):
+        return run_device_generated(args, w, config, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist

@@ -118,7 +118,7 @@ PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
     "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_partition_rows", "cmfb200_nccl_unique_id", "cmfb200_als_create",
     "cmfb200_gram", "cmfb200_set_world", "cmfb200_trim_pool", "cmfb200_debug_poison_smem", "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
     "cmfb200_als_iterate", "cmfb200_als_timed_iterate", "cmfb200_als_set_profile",
-    "cmfb200_serve_create", "cmfb200_serve_destroy", "cmfb200_serve_predict", "cmfb200_serve_topn", "cmfb200_gemm_nt",
+    "cmfb200_als_create_from_device_coo", "cmfb200_als_random_factors", "cmfb200_serve_create", "cmfb200_serve_destroy", "cmfb200_serve_predict", "cmfb200_serve_topn", "cmfb200_gemm_nt",
     "cmfb200_als_read_profile", "cmfb200_als_attach_collective", "cmfb200_als_get_collective", "cmfb200_als_sync", "cmfb200_als_launch_count", "cmfb200_als_local_counts",
 )
 
@@ -199,6 +199,10 @@ def bind_product(lib, dtype):
     lib.cmfb200_als_create.restype = c_int
     lib.cmfb200_als_create.argtypes = [C.POINTER(c_void_p), C.POINTER(lib.AlsOptions), P, P, P, P, P, P]
     lib.cmfb200_als_destroy.restype = None
+    lib.cmfb200_als_create_from_device_coo.restype = c_int
+    lib.cmfb200_als_create_from_device_coo.argtypes = [C.POINTER(c_void_p), C.POINTER(lib.AlsOptions), P, P, P, c_size_t, real, real]
+    lib.cmfb200_als_random_factors.restype = c_int
+    lib.cmfb200_als_random_factors.argtypes = [P, C.c_ulonglong, real]
     lib.cmfb200_gram.restype = c_int
     lib.cmfb200_gram.argtypes = [P, c_int, c_int, P, c_int, C.POINTER(C.c_float)]
     lib.cmfb200_trim_pool.restype = None

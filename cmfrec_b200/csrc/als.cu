@@ -497,6 +497,33 @@ int AlsState::download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, 
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
+namespace {
+__global__ void random_fill_kernel(real_t *F, size_t rows, int ld, int kk, unsigned long long seed, real_t scale, const int_t *to_old)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * (size_t)ld) return;
+    const int c = (int)(i % ld);
+    if (c >= kk || (to_old && to_old[i / ld] < 0)) { F[i] = real_t(0); return; }   // padding columns and padding rows stay zero
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);   // splitmix64 of the element index
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    F[i] = (real_t)(((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0)) * scale;
+}
+}  // namespace
+
+int AlsState::random_factors(unsigned long long seed, real_t scale)
+{
+    const size_t total = (size_t)renA.rows_padded * ldA;
+    if (total) random_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(A.p, (size_t)renA.rows_padded, ldA, cfg.kk, seed, scale,
+                                                                                                  renA.d_to_old.p);
+    if (cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream) != cudaSuccess)
+        return 1;
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
 int AlsState::download_matrix(int which, const real_t *src, int ld, real_t *h, int ldh)
 {
     if (download_rows(src, ld, which ? cfg.m : cfg.n, cfg.kk, which ? renA : renB, h, ldh, stream)) return 1;

@@ -173,6 +173,7 @@ public:
     int upload_factors(const real_t *hA, int lda, const real_t *hbiasA, const real_t *hB, int ldb, const real_t *hbiasB);
     int upload_coordinates(const real_t *hA, const real_t *hB);   // keeps the bias slots already on the device
     int upload_bias(int which, const real_t *hbias);
+    int random_factors(unsigned long long seed, real_t scale);   // A ~ U(0, scale) from a counter hash, B = 0, biases = 0 (device)
     int download_factors(real_t *hA, int lda, real_t *hbiasA, real_t *hB, int ldb, real_t *hbiasB);
     // any device matrix with one row per user (which = 1) / item (0) in device numbering -> host, caller numbering, kk columns
     int download_matrix(int which, const real_t *src, int ld, real_t *h, int ldh);

@@ -368,6 +368,42 @@ int cmfb200_als_create(cmfb200_als **out, const cmfb200_als_options *opt, const 
     return 0;
 }
 
+// The same state from COO triplets ALREADY ON THE DEVICE (ixA / ixB / X: device pointers; X is multiplied by `scale` and, for
+// the explicit model, reduced by `mu`, IN PLACE): both orientations are built, and with world > 1 dealt, on the GPU.  This is how
+// workloads too large to stage on the host are set up (BASELINE config 5: 10^9 entries generated on the device).
+int cmfb200_als_create_from_device_coo(cmfb200_als **out, const cmfb200_als_options *opt, const int_t *d_ixA, const int_t *d_ixB,
+                                       real_t *d_X, size_t nnz, real_t mu, real_t scale)
+{
+    if (!out || !opt || (nnz && (!d_ixA || !d_ixB || !d_X))) return 2;
+    *out = nullptr;
+    if (cmfb200_device_count() < 1) {
+        std::fprintf(stderr, "cmfrec_b200: no CUDA device available; this library has no CPU path.\n");
+        return 1;
+    }
+    if (nnz > (size_t)2147483647) return 2;
+    AlsConfig c;
+    c.implicit = opt->implicit != 0;
+    c.m = opt->m; c.n = opt->n; c.kk = opt->k;
+    c.user_bias = !c.implicit && opt->user_bias; c.item_bias = !c.implicit && opt->item_bias;
+    c.lam_A = opt->lam_A; c.lam_B = opt->lam_B; c.lam_biasA = opt->lam_biasA; c.lam_biasB = opt->lam_biasB;
+    c.scale_lam = opt->scale_lam != 0;
+    c.max_cg_steps = opt->max_cg_steps;
+    c.rank = opt->rank; c.world = opt->world < 1 ? 1 : opt->world;
+    cmfb200_als *s = new cmfb200_als();
+    int rc = s->st.setup_from_coo(c, d_ixA, d_ixB, d_X, nnz, mu, scale, (cudaStream_t)opt->stream, nullptr, opt->nccl_id, nullptr, true);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return 0;
+}
+
+// A filled on the device with uniform values in (0, scale) that depend only on (seed, row, column) -- identical replicas on
+// every rank --, B and the biases zero: a starting point for benchmarks whose factors never exist on the host
+int cmfb200_als_random_factors(cmfb200_als *s, unsigned long long seed, real_t scale)
+{
+    if (!s) return 2;
+    return s->st.random_factors(seed, scale);
+}
+
 void cmfb200_als_destroy(cmfb200_als *s) { delete s; }
 
 int cmfb200_als_set_factors(cmfb200_als *s, const real_t *A, const real_t *biasA, const real_t *B, const real_t *biasB)

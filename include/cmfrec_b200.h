@@ -384,6 +384,12 @@ int cmfb200_partition_rows(const size_t *indptr, int_t rows, int world, int_t *t
 int cmfb200_als_create(cmfb200_als **out, const cmfb200_als_options *opt,
                        const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
                        const size_t *csc_p, const int_t *csc_i, const real_t *csc_v);
+/* the same from COO triplets that are ALREADY ON THE DEVICE (device pointers; d_X is transformed in place to (x - mu) * scale): both
+ * orientations are built -- and with world > 1 dealt to the ranks -- on the GPU.  nnz <= INT_MAX. */
+int cmfb200_als_create_from_device_coo(cmfb200_als **out, const cmfb200_als_options *opt, const int_t *d_ixA, const int_t *d_ixB,
+                                       real_t *d_X, size_t nnz, real_t mu, real_t scale);
+/* A ~ U(0, scale) from a counter-based hash of (seed, element) on the device (identical on every rank), B and biases zero */
+int cmfb200_als_random_factors(cmfb200_als *s, unsigned long long seed, real_t scale);
 void cmfb200_als_destroy(cmfb200_als *s);
 /* factors in caller numbering, row-major [m x k] / [n x k]; bias arrays may be NULL */
 int cmfb200_als_set_factors(cmfb200_als *s, const real_t *A, const real_t *biasA, const real_t *B, const real_t *biasB);
