@@ -212,7 +212,7 @@ def time_reference(w, data, steps, warmup, nthreads):
 
 def generate_cfg5_on_device(torch, m, n, seed):
     """COO triplets of BASELINE config 5 on the current CUDA device (every rank generates the same arrays): row degrees
-    lognormal with mean 100, columns Zipf-like (log-uniform ranks, then scattered over the ids by an affine map),
+    lognormal with mean 100, columns Zipf-like (shifted, exponent 1; ranks scattered over the ids by an affine map),
     values ceil(lognormal(1, 1.5)) -- SURVEY.md 8(d).  Returns int32 rows, int32 cols, float32 values."""
     import math
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -226,13 +226,16 @@ def generate_cfg5_on_device(torch, m, n, seed):
     cols = torch.empty(nnz, dtype=torch.int32, device=dev)
     vals = torch.empty(nnz, dtype=torch.float32, device=dev)
     step = 1 << 26
+    r0 = max(1.0, n / 10000.0)
     mult = 2654435761 % n
     while math.gcd(mult, n) != 1:
         mult += 1
     for s in range(0, nnz, step):
         e = min(nnz, s + step)
         u = torch.rand(e - s, generator=g, device=dev, dtype=torch.float64)
-        c = torch.exp(u * math.log(n)).to(torch.int64).sub_(1).clamp_(0, n - 1)
+        # shifted Zipf, p(rank) ~ 1 / (rank + r0): the most popular item holds ~0.1 % of the entries (LastFM-360K's top artist
+        # holds 0.45 %), not the 7 % an unshifted exponent-1 law over 10^6 items would give it
+        c = (torch.exp(u * math.log((n + r0) / r0)) * r0 - r0).to(torch.int64).clamp_(0, n - 1)
         cols[s:e] = ((c * mult + 12345) % n).to(torch.int32)
         z = torch.randn(e - s, generator=g, device=dev)
         vals[s:e] = torch.ceil(torch.exp(1.0 + 1.5 * z)).clamp_(1.0, 1e6)
