@@ -540,6 +540,19 @@ def main():
                     launches_timed=int(kernel_launches), algorithmic_bytes_per_launch=bytes_per_launch,
                     kernel_share_of_step=kernel_ms / total_ms if total_ms else None, peak_source=peak_src,
                     B_sweep_ms=kt[0].value / max(kc[0].value, 1), A_sweep_ms=kt[1].value / max(kc[1].value, 1))
+    if not w["use_cg"]:
+        # exact (Cholesky) sweeps are bound by the tensor pipe, not by HBM: algorithmic flop of the normal matrices and their
+        # factorisations (nnz k'(k'+1) + rows (k'^3 / 3 + 2 k'^2) per half-sweep) against the measured GEMM peak
+        k1 = w["k"] + (0 if w["implicit"] else 1)
+        flop = 2 * nnz * k1 * (k1 + 1) + (m + n) * (k1 ** 3 / 3.0 + 2 * k1 * k1)
+        fp = json.load(open(os.path.join(ROOT, "profiles", "r2_fp_peaks.json")))
+        tpeak = fp["fp64_tflops"] if w["dtype"] == "f64" else fp["tf32_tflops"]
+        ach = flop / 2.0 / world / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        roofline.update(bound="tensor", achieved=ach, peak=tpeak, unit="TFLOP/s", frac=ach / tpeak,
+                        kernel="chol_dmma_build_kernel + chol_dmma_factor_kernel" if w["dtype"] == "f64" else "nm_sweep_kernel",
+                        algorithmic_flop_per_launch=flop / 2.0 / world, hbm_model_frac=achieved / peak,
+                        peak_source="profiles/r2_fp_peaks.json: measured %s GEMM (torch.matmul 8192^3); the fp32 kernel issues 3 TF32 "
+                                    "products per algorithmic one" % ("FP64" if w["dtype"] == "f64" else "TF32"))
     L.cmfb200_als_destroy(hnd)
     del flush
 
