@@ -19,8 +19,12 @@
 #include "cg_row.cuh"
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
+#ifndef CMF_TM_ENABLE
+#define CMF_TM_ENABLE 0   // tensor memory as a second cache tier: measured neutral (profiles/README.md), compiled out; make EXTRA=-DCMF_TM_ENABLE=1
+#endif
 #ifndef CMF_RES_DEPTH
 #define CMF_RES_DEPTH 4   // steps the streamed gathers run ahead of the arithmetic (8-lane layouts)
 #endif
@@ -40,6 +44,44 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
 {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+
+// ---- tensor memory as a second cache tier (fp32, 8 coordinates per lane): the 256 KB of TMEM of an SM are idle in this
+// kernel, a tcgen05.ld costs ~12 cycles against the several hundred of an L2 gather, and it does not go through the
+// LSU pipe the gathers saturate.  A warp reaches the 32 TMEM lanes of its quarter (warp id mod 4); thread t keeps its 8
+// registers of a step in 8 consecutive columns of lane t.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// four steps (32 columns) at once
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[4][8])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[t][e] = __uint_as_float(r[t * 8 + e]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t, const double (&)[4]) {}      // fp64 layouts do not use the tier
+template <int C> __device__ __forceinline__ void tmem_st8(uint32_t, const double (&)[C]) {}
+template <int C> __device__ __forceinline__ void tmem_st8(uint32_t, const float (&)[C]) {}
+constexpr int kTmemColsPerBlock = 256;   // two blocks per SM share the 512 columns
+constexpr int kTmemColsPerWarp = 128;    // warps w and w + 4 share a lane quarter
 
 // ---------------------------------------------------------------------------------------------------------
 // Gather policy: this warp's entries come from its shared-memory region (first `cap` of them) or from L2
@@ -71,6 +113,12 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     int nnz;          // entries in this warp's share
     int gw, GW;       // index of this warp in its team / number of warps in the team (all blocks of a cluster)
     int lane, g, l, gi;
+    // tensor-memory tier: the first tm_chunks full 32-entry chunks BEYOND the resident part are kept in TMEM by the residual
+    // pass and read from there by the later passes (fp32, C == 8, L <= 16 only; 0 = off)
+    static constexpr bool TM_OK = CMF_TM_ENABLE && sizeof(T) == 4 && C == 8 && L <= 16;
+    static constexpr int TM_CHUNK_COLS = L * 8;   // a chunk is L steps of 8 columns
+    uint32_t tm_addr = 0;
+    int tm_chunks = 0;
 
     __device__ __forceinline__ ResidentGather(const CgSweepParams &p_, T *region, int cap_, int gw_, int GW_)
         : p(p_), rows(region), xs(region + (size_t)cap_ * RS), cap(cap_), beg(0), nnz(0), gw(gw_), GW(GW_)
@@ -216,26 +264,64 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     // register buffers, no load issued twice) and the (column, value) pairs of the next chunk are fetched while the
     // current one is processed: the streamed part is bound by L2 latency, i.e. by the bytes in flight per warp.
     static constexpr int D = (C <= 8 && L >= 4) ? (CMF_RES_DEPTH < L ? CMF_RES_DEPTH : L) : 2;
+    // one full 32-entry chunk streamed from L2: L steps in a straight line, every buffer index a compile-time constant;
+    // STORE: the rows are also left in tensor memory (chunk `ch` of the tier) for the later passes
+    template <int KIND, bool FULLW, bool STORE>
+    __device__ __forceinline__ void chunk_streamed(int col_r, T x_r, int ch, const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
+    {
+        T v[D][C], x[D], o[D];
+#pragma unroll
+        for (int d = 0; d < D - 1; d++) load_streamed<FULLW>(col_r, x_r, d * G + gi, v[d], x[d], o[d]);
+#pragma unroll
+        for (int t = 0; t < L; t++) {
+            if (t + D - 1 < L)
+                load_streamed<FULLW>(col_r, x_r, (t + D - 1) * G + gi, v[(t + D - 1) % D], x[(t + D - 1) % D], o[(t + D - 1) % D]);
+            step<KIND>(v[t % D], x[t % D], o[t % D], vec, vecb, acc, accb);
+            if constexpr (STORE) tmem_st8(tm_addr + (uint32_t)(ch * TM_CHUNK_COLS + t * 8), v[t % D]);
+        }
+    }
+
     template <int KIND, bool FULLW>
     __device__ __forceinline__ void pass_streamed(const T (&vec)[C], T vecb, T (&acc)[C], T &accb) const
     {
+        constexpr bool FIRST = KIND == kExplicitResidual || KIND == kImplicitResidual;   // the pass that fills the TMEM tier
         int col_r, col_n = -1;
         T x_r, x_n = T(0);
         load_chunk<KIND>(cap, col_r, x_r);
-        for (int e0 = cap; e0 < nnz; e0 += 32) {
+        int e0 = cap;
+        if constexpr (TM_OK) {
+            // ---- the first tm_chunks full chunks: streamed and stored by the residual pass, read from tensor memory afterwards
+            for (int ch = 0; ch < tm_chunks && nnz - e0 >= 32; ch++, e0 += 32) {
+                if (e0 + 32 < nnz) load_chunk<KIND>(e0 + 32, col_n, x_n);
+                if constexpr (FIRST) {
+                    chunk_streamed<KIND, FULLW, true>(col_r, x_r, ch, vec, vecb, acc, accb);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < L / 4; h++) {   // four steps per tcgen05.ld
+                        float v4[4][8];
+                        tmem_ld32(tm_addr + (uint32_t)(ch * TM_CHUNK_COLS + h * 32), v4);
+#pragma unroll
+                        for (int t4 = 0; t4 < 4; t4++) {
+                            const int ent = (h * 4 + t4) * G + gi;
+                            const int col = __shfl_sync(CMF_FULL_MASK, col_r, ent);
+                            const T x = __shfl_sync(CMF_FULL_MASK, x_r, ent);
+                            step<KIND>(v4[t4], x, col >= 0 ? T(1) : T(0), vec, vecb, acc, accb);
+                        }
+                    }
+                }
+                col_r = col_n;
+                x_r = x_n;
+                col_n = -1;
+                x_n = T(0);
+            }
+            if (FIRST && tm_chunks > 0) tmem_wait_st();
+        }
+        // ---- everything else from L2 on every pass
+        for (; e0 < nnz; e0 += 32) {
             if (e0 + 32 < nnz) load_chunk<KIND>(e0 + 32, col_n, x_n);
             const int left = nnz - e0;
             if (left >= 32) {
-                // full chunk: L steps in a straight line, every buffer index a compile-time constant
-                T v[D][C], x[D], o[D];
-#pragma unroll
-                for (int d = 0; d < D - 1; d++) load_streamed<FULLW>(col_r, x_r, d * G + gi, v[d], x[d], o[d]);
-#pragma unroll
-                for (int t = 0; t < L; t++) {
-                    if (t + D - 1 < L)
-                        load_streamed<FULLW>(col_r, x_r, (t + D - 1) * G + gi, v[(t + D - 1) % D], x[(t + D - 1) % D], o[(t + D - 1) % D]);
-                    step<KIND>(v[t % D], x[t % D], o[t % D], vec, vecb, acc, accb);
-                }
+                chunk_streamed<KIND, FULLW, false>(col_r, x_r, 0, vec, vecb, acc, accb);
             } else {
                 // last, partial chunk of the share
                 const int nst = (left + G - 1) / G;
@@ -293,6 +379,7 @@ struct ResidentPlan {
     // cumulative slot counts (a slot = one thread block's worth of rows)
     int s8, s4, s2, n_slots;
     int cap;   // resident entries per warp
+    int tmem;  // use tensor memory as a second cache tier (at most two blocks per SM then)
 };
 
 template <typename T, int C, int L> struct ResidentSmem {
@@ -303,7 +390,7 @@ template <typename T, int C, int L> struct ResidentSmem {
 
 template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW>
 __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, size_t beg, int nnz, T *stripes, const T *gram,
-                                             T *region, int cap, int w)
+                                             T *region, int cap, int w, uint32_t tm_addr, int tm_chunks)
 {
     typedef ResidentGather<T, C, L, TW == 8 || TW == 1> Gat;   // 2- and 4-warp teams only get rows that fit
     const int team = w / TW, wt = w % TW;
@@ -312,6 +399,8 @@ __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, si
     CgRow<T, C, L, MODEL, TW, GRAM_SMEM> s(p, stripes + (size_t)(team * TW) * ResidentSmem<T, C, L>::STRIPE, gram, wt, bar_id);
     if (nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows)) {
         Gat gat(p, region, cap, wt, TW);
+        gat.tm_addr = tm_addr;
+        gat.tm_chunks = tm_chunks;
         gat.begin(beg, nnz);
         gat.stage();
         s.solve(row, nnz, gat);
@@ -344,6 +433,30 @@ __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSwee
     const int w = threadIdx.x >> 5;
     T *region = regions + (size_t)w * rp.cap * (Gat::RS + 2);
     Gat(p, region, rp.cap, 0, 1).clear_region();
+    // tensor-memory tier (see tmem_st8): 256 columns per block, 128 per warp
+    __shared__ uint32_t tmem_slot;
+    uint32_t tm_addr = 0;
+    int tm_chunks = 0;
+    if constexpr (Gat::TM_OK) {
+        // A kernel that contains tcgen05.alloc holds the SM's allocation permit from the moment a block starts: no second block
+        // of it becomes resident until the permit is relinquished (measured: without this the kernel runs one block per SM at
+        // half the speed) -- so relinquish it even when the tier is switched off at run time.
+        if (w == 0) {
+            if (rp.tmem)
+                asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(&tmem_slot)),
+                             "r"((uint32_t)kTmemColsPerBlock)
+                             : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        if (rp.tmem) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tm_addr = tmem_slot + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * kTmemColsPerWarp);
+            tm_chunks = kTmemColsPerWarp / Gat::TM_CHUNK_COLS;
+        }
+    }
 
     // order-list position of the row this warp works on in a slot (-1: none)
     auto decode = [&](int slot) -> int {
@@ -382,17 +495,25 @@ __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSwee
         }
         if (row0 >= 0) {
             const int nnz = (int)(end0 - beg0);
-            if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+            if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
 #ifdef CMF_RES_TEAMS   // 2- and 4-warp teams (CMFB200_RES_MODE=0, measured slower): compiled on request only
-            else if (slot < rp.s4) resident_row<T, C, L, MODEL, GRAM_SMEM, 4>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
-            else if (slot < rp.s2) resident_row<T, C, L, MODEL, GRAM_SMEM, 2>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+            else if (slot < rp.s4) resident_row<T, C, L, MODEL, GRAM_SMEM, 4>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
+            else if (slot < rp.s2) resident_row<T, C, L, MODEL, GRAM_SMEM, 2>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
 #endif
-            else resident_row<T, C, L, MODEL, GRAM_SMEM, 1>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w);
+            else resident_row<T, C, L, MODEL, GRAM_SMEM, 1>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
         }
         row0 = row1;
         beg0 = beg1;
         end0 = end1;
         row1 = row2;
+    }
+    if constexpr (Gat::TM_OK) {
+        if (rp.tmem) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (w == 0)
+                asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((uint32_t)kTmemColsPerBlock) : "memory");
+        }
     }
 }
 
@@ -527,7 +648,7 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     // thread blocks per SM (default two); the driver reserves 1 KB per block
     const int bps = env_int("CMFB200_RES_BPS", MINB) == 1 ? 1 : MINB;
-    size_t per_block = (size_t)smem_sm / bps - 1024;
+    size_t per_block = (size_t)smem_sm / bps - 1024 - 64;   // 64: the kernel's few static words (TMEM slot) must fit beside it
     if (per_block > (size_t)smem_optin) per_block = (size_t)smem_optin;
 
     // mode 1 (default, measured fastest): one warp per row with a shared-memory cache; mode 0: teams sized so that
@@ -572,6 +693,7 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     }
     ResidentPlan rp;
     rp.cap = cap1;
+    rp.tmem = (Gat::TM_OK && env_int("CMFB200_RES_TMEM", 1) != 0) ? 1 : 0;
     if (mode == 1) {
         // one warp per row as in the direct kernel, the first cap1 entries of every row resident, the rest streamed;
         // rows of >= 1024 entries get a thread block, rows of >= 8192 a cluster of 8
@@ -619,6 +741,10 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kW * 32, smem1);
         if (occ < 1) return 1;
+        // the occupancy calculator answers 1 for any kernel that contains tcgen05.alloc (it cannot know how many columns a block
+        // takes); registers (128 x 256) and shared memory (<= half an SM) are sized for two blocks, which take 256 columns each
+        if (Gat::TM_OK) occ = env_int("CMFB200_RES_TMEM_BPS", 512 / kTmemColsPerBlock);
+        if (env_int("CMFB200_RES_DEBUG", 0)) std::fprintf(stderr, "[resident] occ=%d smem1=%zu per_block=%zu cap1=%d tmem=%d\n", occ, smem1, per_block, cap1, rp.tmem);
         long long grid = (long long)sms * occ;
         if (grid > rp.n_slots) grid = rp.n_slots;
         kern<<<(unsigned)grid, kW * 32, smem1, stream>>>(p, rp);
