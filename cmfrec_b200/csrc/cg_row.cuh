@@ -120,7 +120,7 @@ template <typename T, int C, int L, int TW> struct TeamScratch {
 //             q = w_user C^T u_i + w_implicit sum_e Bi_e).
 constexpr int kModelExplicit = 0, kModelImplicit = 1, kModelCollective = 2;
 
-template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 1> struct CgRow {
+template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 1, bool COOP = false> struct CgRow {
     static constexpr bool IMPLICIT = MODEL == kModelImplicit;
     static constexpr bool HAS_Q = MODEL != kModelExplicit;
     static_assert(CL == 1 || TW > 1, "a cluster team is made of whole thread blocks");
@@ -137,6 +137,12 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
     T *cl_buf = nullptr;   // CL > 1 only
     int cl_phase = 0;
     int cl_rank = 0;       // rank of this block in the cluster (CL > 1)
+    // COOP (one warp per row, constant matrix too large for shared memory, 256-thread blocks whose 8 warps work on 8 rows in
+    // lockstep): the 8 rows' products with the constant matrix are computed TOGETHER, thread c taking column c for all 8
+    // vectors, so the matrix is read once per 8 rows and pass instead of once per row and pass (k = 256: 256 KB each time)
+    static constexpr int kCoopRows = 8, kCoopBar = 8;
+    T *coop_base = nullptr;   // scratch stripes of the block's 8 warps: [8][coop_stride], vector at 0, product at KP
+    int coop_stride = 0;
 
     __device__ __forceinline__ CgRow(const CgSweepParams &p_, T *scratch, const T *gram_, int warp_in_team, int bar_id_)
         : p(p_), red(scratch), vec_sm(scratch + (TW > 1 ? 2 * TW * Scr::RED_STRIDE : 0)), gram(gram_), wt(warp_in_team),
@@ -234,6 +240,156 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
                     if (c < kk) acc[j] = fma(__ldg(mrow + c), s, acc[j]);
                 }
             }
+        }
+    }
+
+    // acc += sign * gram * vec for the 8 rows the block's warps hold; EVERY thread of the block must call it (warps without a
+    // live row pass active = false)
+    __device__ __forceinline__ void coop_gram(const T (&vec)[C], bool active, T sign, T (&acc)[C])
+    {
+        static_assert(!COOP || (sizeof(T) == 4 && Lay::KP == 256 && TW == 1 && CL == 1 && !GRAM_SMEM), "COOP layout");
+        const int kk = p.kk, tid = threadIdx.x, w = tid >> 5;
+        T *mine = coop_base + (size_t)w * coop_stride;
+#pragma unroll
+        for (int j = 0; j < C; j++) mine[Lay::col(l, j)] = active ? vec[j] : T(0);
+        asm volatile("bar.sync %0, %1;" ::"r"(kCoopBar), "r"(kCoopRows * 32) : "memory");
+        if (tid < kk) {
+            T y[kCoopRows];
+#pragma unroll
+            for (int r = 0; r < kCoopRows; r++) y[r] = T(0);
+            const T *gcol = gram + tid;
+            int d = 0;
+            for (; d + 4 <= kk; d += 4) {
+                const T g0 = __ldg(gcol + (size_t)d * kk), g1 = __ldg(gcol + (size_t)(d + 1) * kk), g2 = __ldg(gcol + (size_t)(d + 2) * kk),
+                        g3 = __ldg(gcol + (size_t)(d + 3) * kk);
+#pragma unroll
+                for (int r = 0; r < kCoopRows; r++) {
+                    const float4 vv = *reinterpret_cast<const float4 *>(coop_base + (size_t)r * coop_stride + d);
+                    y[r] = fma(g0, vv.x, y[r]);
+                    y[r] = fma(g1, vv.y, y[r]);
+                    y[r] = fma(g2, vv.z, y[r]);
+                    y[r] = fma(g3, vv.w, y[r]);
+                }
+            }
+            for (; d < kk; d++) {
+                const T gv = __ldg(gcol + (size_t)d * kk);
+#pragma unroll
+                for (int r = 0; r < kCoopRows; r++) y[r] = fma(gv, coop_base[(size_t)r * coop_stride + d], y[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kCoopRows; r++) coop_base[(size_t)r * coop_stride + Lay::KP + tid] = y[r];
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(kCoopBar), "r"(kCoopRows * 32) : "memory");
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                const int c = Lay::col(l, j);
+                if (c < kk) acc[j] = fma(sign, mine[Lay::KP + c], acc[j]);
+            }
+        }
+    }
+
+    // a warp of a COOP block that has no row to solve in this slot still takes part in the block's products
+    __device__ __forceinline__ void coop_idle()
+    {
+        T z[C], acc[C];
+#pragma unroll
+        for (int j = 0; j < C; j++) z[j] = acc[j] = T(0);
+        for (int i = 0; i < 1 + p.max_cg_steps; i++) coop_gram(z, false, T(1), acc);
+    }
+
+    // The same solve with the constant-matrix products shared by the block (COOP): every warp makes exactly
+    // 1 + max_cg_steps calls of coop_gram, rows that have met an exit threshold go on as passengers without touching
+    // their state -- the iterates are those of solve().
+    template <typename Gather> __device__ void solve_coop(int row, int nnz, Gather &gather)
+    {
+        const int kk = p.kk;
+        T *frow = p.F + (size_t)row * (size_t)p.ldF;
+        T a[C], r[C], pv[C], acc[C];
+        T ab = T(0), rb = T(0), pb = T(0), accb = T(0);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int c = Lay::col(l, j);
+            a[j] = (c < kk) ? frow[c] : T(0);
+        }
+        const bool hb = !IMPLICIT && p.solve_bias;
+        if (hb) ab = p.bias_start_one ? T(1) : p.Fbias[row];
+        T lam = p.lam, lam_last = p.lam_last;
+        if (!IMPLICIT && p.scale_lam && nnz > 0) {
+            lam *= (T)nnz;
+            if (!p.scale_bias_const) lam_last *= (T)nnz;
+        }
+#pragma unroll
+        for (int j = 0; j < C; j++) acc[j] = T(0);
+        accb = T(0);
+        coop_gram(a, true, T(-1), acc);
+        gather.template pass<IMPLICIT ? kImplicitResidual : kExplicitResidual>(a, ab, acc, accb);
+        combine(acc, accb);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int c = Lay::col(l, j);
+            r[j] = (c < kk) ? fma(-lam, a[j], acc[j]) : T(0);
+            if (p.qvec && c < kk) r[j] += p.qvec[(size_t)row * (size_t)p.ldq + c];
+        }
+        if (hb) {
+            rb = fma(-lam, ab, accb);
+            if (lam != lam_last) rb -= (lam_last - lam) * ab;
+        }
+        T r_old = dot_full(r, r, rb, rb);
+        bool changed = false;
+        bool active = !(r_old <= T(1e-12));
+#pragma unroll
+        for (int j = 0; j < C; j++) pv[j] = r[j];
+        pb = rb;
+        for (int step = 0; step < p.max_cg_steps; step++) {
+#pragma unroll
+            for (int j = 0; j < C; j++) acc[j] = T(0);
+            accb = T(0);
+            coop_gram(pv, active, T(1), acc);
+            if (active) {   // warp-uniform
+                gather.template pass<IMPLICIT ? kImplicitAp : kExplicitAp>(pv, pb, acc, accb);
+                combine(acc, accb);
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int c = Lay::col(l, j);
+                    acc[j] = (c < kk) ? fma(lam, pv[j], acc[j]) : T(0);
+                }
+                if (hb) {
+                    accb = fma(lam, pb, accb);
+                    if (lam != lam_last) accb += (lam_last - lam) * pb;
+                } else {
+                    accb = T(0);
+                }
+                const T alpha = r_old / dot_full(pv, acc, pb, accb);
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    a[j] = fma(alpha, pv[j], a[j]);
+                    r[j] = fma(-alpha, acc[j], r[j]);
+                }
+                ab = fma(alpha, pb, ab);
+                rb = fma(-alpha, accb, rb);
+                changed = true;
+                const T r_new = dot_full(r, r, rb, rb);
+                if (r_new <= T(1e-8)) {
+                    active = false;
+                } else {
+                    const T beta = r_new / r_old;
+#pragma unroll
+                    for (int j = 0; j < C; j++) pv[j] = fma(beta, pv[j], r[j]);
+                    pb = fma(beta, pb, rb);
+                    r_old = r_new;
+                }
+            }
+        }
+        if (g == 0 && wt == 0) {
+            if (changed) {
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int c = Lay::col(l, j);
+                    if (c < kk) frow[c] = a[j];
+                }
+            }
+            if (hb && l == 0 && (changed || p.bias_start_one)) p.Fbias[row] = ab;
         }
     }
 

@@ -388,24 +388,37 @@ template <typename T, int C, int L> struct ResidentSmem {
     static constexpr int STRIPE = 2 * RED_STRIDE + Lay::KP;   // scratch per warp; a team of TW warps owns TW stripes
 };
 
+// one warp per row with the constant matrix in global memory and rows as wide as the block has threads: the block's 8 warps
+// share every product with the constant matrix (CgRow::coop_gram)
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW> struct CoopMode {
+    static constexpr bool value = TW == 1 && MODEL != kModelExplicit && !GRAM_SMEM && sizeof(T) == 4 && Layout<T, C, L>::KP == kW * 32;
+};
+
 template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW>
 __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, size_t beg, int nnz, T *stripes, const T *gram,
                                              T *region, int cap, int w, uint32_t tm_addr, int tm_chunks)
 {
     typedef ResidentGather<T, C, L, TW == 8 || TW == 1> Gat;   // 2- and 4-warp teams only get rows that fit
+    constexpr bool COOP = CoopMode<T, C, L, MODEL, GRAM_SMEM, TW>::value;
     const int team = w / TW, wt = w % TW;
     // one named barrier per (team size, team): a block's teams run ahead of each other by whole slots
     const int bar_id = (TW == 8) ? 1 : (TW == 4) ? 2 + team : (TW == 2) ? 4 + team : 0;
-    CgRow<T, C, L, MODEL, TW, GRAM_SMEM> s(p, stripes + (size_t)(team * TW) * ResidentSmem<T, C, L>::STRIPE, gram, wt, bar_id);
-    if (nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows)) {
+    CgRow<T, C, L, MODEL, TW, GRAM_SMEM, 1, COOP> s(p, stripes + (size_t)(team * TW) * ResidentSmem<T, C, L>::STRIPE, gram, wt, bar_id);
+    if constexpr (COOP) {
+        s.coop_base = stripes;
+        s.coop_stride = ResidentSmem<T, C, L>::STRIPE;
+    }
+    if (row >= 0 && (nnz > 0 || (MODEL != kModelExplicit && p.solve_all_rows))) {
         Gat gat(p, region, cap, wt, TW);
         gat.tm_addr = tm_addr;
         gat.tm_chunks = tm_chunks;
         gat.begin(beg, nnz);
         gat.stage();
-        s.solve(row, nnz, gat);
+        if constexpr (COOP) s.solve_coop(row, nnz, gat);
+        else s.solve(row, nnz, gat);
     } else {
-        s.empty_row(row);
+        if constexpr (COOP) s.coop_idle();
+        if (row >= 0) s.empty_row(row);
     }
     team_barrier<TW>(bar_id);   // nobody of the team reuses scratch or regions before everybody is done with the row
 }
@@ -493,7 +506,7 @@ __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSwee
             beg1 = p.X.ptr[row1];
             end1 = p.X.ptr[row1 + 1];
         }
-        if (row0 >= 0) {
+        if (row0 >= 0 || (CoopMode<T, C, L, MODEL, GRAM_SMEM, 1>::value && slot >= rp.s2)) {
             const int nnz = (int)(end0 - beg0);
             if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
 #ifdef CMF_RES_TEAMS   // 2- and 4-warp teams (CMFB200_RES_MODE=0, measured slower): compiled on request only
