@@ -247,44 +247,59 @@ template <typename T, int C, int L, int MODEL, int TW, bool GRAM_SMEM, int CL = 
     // live row pass active = false)
     __device__ __forceinline__ void coop_gram(const T (&vec)[C], bool active, T sign, T (&acc)[C])
     {
-        static_assert(!COOP || (sizeof(T) == 4 && Lay::KP == 256 && TW == 1 && CL == 1 && !GRAM_SMEM), "COOP layout");
+        constexpr int KP = Lay::KP;
+        constexpr int PARTS = (kCoopRows * 32) / KP;     // threads per column: the rows of the matrix are split between them
+        static_assert(!COOP || ((KP == 256 || KP == 128) && TW == 1 && CL == 1 && !GRAM_SMEM), "COOP layout");
+        constexpr int VN = VecOf<T>::N;
+        typedef typename VecOf<T>::type Vec;
         const int kk = p.kk, tid = threadIdx.x, w = tid >> 5;
         T *mine = coop_base + (size_t)w * coop_stride;
+        if (g == 0) {
 #pragma unroll
-        for (int j = 0; j < C; j++) mine[Lay::col(l, j)] = active ? vec[j] : T(0);
+            for (int j = 0; j < C; j++) mine[Lay::col(l, j)] = active ? vec[j] : T(0);
+        }
         asm volatile("bar.sync %0, %1;" ::"r"(kCoopBar), "r"(kCoopRows * 32) : "memory");
-        if (tid < kk) {
+        const int c = tid % KP, part = tid / KP;
+        if (c < kk) {
             T y[kCoopRows];
 #pragma unroll
             for (int r = 0; r < kCoopRows; r++) y[r] = T(0);
-            const T *gcol = gram + tid;
-            int d = 0;
-            for (; d + 4 <= kk; d += 4) {
-                const T g0 = __ldg(gcol + (size_t)d * kk), g1 = __ldg(gcol + (size_t)(d + 1) * kk), g2 = __ldg(gcol + (size_t)(d + 2) * kk),
-                        g3 = __ldg(gcol + (size_t)(d + 3) * kk);
+            const T *gcol = gram + c;
+            // this thread's share of the rows of the matrix, in whole vectors
+            const int per = ((kk + PARTS * VN - 1) / (PARTS * VN)) * VN;
+            int d = part * per;
+            const int dend = min(kk, d + per);
+            for (; d + VN <= dend; d += VN) {
+                T gv[VN];
+#pragma unroll
+                for (int e = 0; e < VN; e++) gv[e] = __ldg(gcol + (size_t)(d + e) * kk);
 #pragma unroll
                 for (int r = 0; r < kCoopRows; r++) {
-                    const float4 vv = *reinterpret_cast<const float4 *>(coop_base + (size_t)r * coop_stride + d);
-                    y[r] = fma(g0, vv.x, y[r]);
-                    y[r] = fma(g1, vv.y, y[r]);
-                    y[r] = fma(g2, vv.z, y[r]);
-                    y[r] = fma(g3, vv.w, y[r]);
+                    const Vec vv = *reinterpret_cast<const Vec *>(coop_base + (size_t)r * coop_stride + d);
+                    const T *pv = reinterpret_cast<const T *>(&vv);
+#pragma unroll
+                    for (int e = 0; e < VN; e++) y[r] = fma(gv[e], pv[e], y[r]);
                 }
             }
-            for (; d < kk; d++) {
+            for (; d < dend; d++) {
                 const T gv = __ldg(gcol + (size_t)d * kk);
 #pragma unroll
                 for (int r = 0; r < kCoopRows; r++) y[r] = fma(gv, coop_base[(size_t)r * coop_stride + d], y[r]);
             }
 #pragma unroll
-            for (int r = 0; r < kCoopRows; r++) coop_base[(size_t)r * coop_stride + Lay::KP + tid] = y[r];
+            for (int r = 0; r < kCoopRows; r++) coop_base[(size_t)r * coop_stride + KP * (1 + part) + c] = y[r];
         }
         asm volatile("bar.sync %0, %1;" ::"r"(kCoopBar), "r"(kCoopRows * 32) : "memory");
         if (active) {
 #pragma unroll
             for (int j = 0; j < C; j++) {
-                const int c = Lay::col(l, j);
-                if (c < kk) acc[j] = fma(sign, mine[Lay::KP + c], acc[j]);
+                const int cc = Lay::col(l, j);
+                if (cc < kk) {
+                    T t = mine[KP + cc];
+#pragma unroll
+                    for (int q = 1; q < PARTS; q++) t += mine[KP * (1 + q) + cc];
+                    acc[j] = fma(sign, t, acc[j]);
+                }
             }
         }
     }

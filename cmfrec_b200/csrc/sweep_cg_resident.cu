@@ -391,7 +391,10 @@ template <typename T, int C, int L> struct ResidentSmem {
 // one warp per row with the constant matrix in global memory and rows as wide as the block has threads: the block's 8 warps
 // share every product with the constant matrix (CgRow::coop_gram)
 template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW> struct CoopMode {
-    static constexpr bool value = TW == 1 && MODEL != kModelExplicit && !GRAM_SMEM && sizeof(T) == 4 && Layout<T, C, L>::KP == kW * 32;
+    static constexpr int KP = Layout<T, C, L>::KP;
+    // the 8 vectors and the (256 / KP) x 8 partial products must fit the 8 scratch stripes
+    static constexpr bool value = TW == 1 && MODEL != kModelExplicit && !GRAM_SMEM && (KP == 256 || KP == 128) &&
+                                  KP + (kW * 32 / KP) * KP <= ResidentSmem<T, C, L>::STRIPE;
 };
 
 template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW>
@@ -677,8 +680,11 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
     // The constant matrix goes to shared memory whenever it fits (every row reads all of it on every pass); what is
     // left is the cache of gathered rows.  In mode 1 the cache may be small or empty (wide rows): the rest of every
     // share is streamed through the pipelined gather, and shared memory that is not asked for stays L1.
-    const bool gram_smem =
-        MODEL != kModelExplicit && (mode == 1 ? fixed1 + gram_bytes + 1024 <= per_block : gram_bytes <= per_block / 3);
+    // (KP = 128 with the matrix in GLOBAL memory is served by the block-shared products, CgRow::coop_gram, and leaves the
+    // 64 KB to the row cache: CMFB200_RES_GRAM_GLOBAL=1)
+    const bool coop_capable = (Lay::KP == 128 || Lay::KP == 256);
+    const bool gram_smem = MODEL != kModelExplicit && !(coop_capable && env_int("CMFB200_RES_GRAM_GLOBAL", 0) != 0) &&
+                           (mode == 1 ? fixed1 + gram_bytes + 1024 <= per_block : gram_bytes <= per_block / 3);
     if (!gram_smem) gram_bytes = 0;
     if (fixed1 + gram_bytes >= per_block) return 3;
     int cap1 = (int)((per_block - fixed1 - gram_bytes) / (kW * Gat::kEntryBytes)) & ~7;

@@ -27,7 +27,9 @@
 // Roofline: FP64 tensor throughput, nnz * (kd+1)^2 + rows * (kd+1)^3 / 3 flop per half-sweep against the measured
 // DGEMM peak (profiles/r2_fp_peaks.json).  See DESIGN.md.
 #include "cg_row.cuh"
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 namespace cmfb200 {
 
@@ -102,11 +104,47 @@ template <int NTR, int R, typename F> __device__ __forceinline__ void dm_dispatc
     }
 }
 
+constexpr int DM_SEG = 4096;   // stored entries per unit of a long row
+
+// Long rows (the first n_split rows of a batch, rows being sorted by decreasing length) are cut into segments of DM_SEG
+// entries so that no single thread block carries a 40,000-entry row: prefix[i] = first unit of row i (device array,
+// n_split + 1 entries); the rows behind them are one unit each.
+struct DmSplit {
+    const int *prefix;
+    int n_split, units_split;
+    __device__ __forceinline__ void locate(int unit, int &ms, int &seg) const
+    {
+        if (unit >= units_split) {
+            ms = n_split + (unit - units_split);
+            seg = 0;
+            return;
+        }
+        int lo = 0, hi = n_split - 1;   // last i with prefix[i] <= unit
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (prefix[mid] <= unit) lo = mid;
+            else hi = mid - 1;
+        }
+        ms = lo;
+        seg = unit - prefix[lo];
+    }
+    __device__ __forceinline__ void units_of(int ms, int &first, int &count) const
+    {
+        if (ms >= n_split) {
+            first = units_split + (ms - n_split);
+            count = 1;
+        } else {
+            first = prefix[ms];
+            count = prefix[ms + 1] - first;
+        }
+    }
+};
+
 // ======================================================================= BUILD
 // rows plan.order[slot0 .. slot0 + nslots) -> tiles of their extended normal matrices in ws[slot - slot0]
 template <int NTR, int MODEL, int BPS>
 __global__ void __launch_bounds__(DmCfg<NTR>::NT, BPS)
-chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nslots, double *__restrict__ ws)
+chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nunits, DmSplit sp, double *__restrict__ ws)
 {
     typedef DmCfg<NTR> Cfg;
     constexpr int NT = Cfg::NT, LD = Cfg::LD, ROWS = Cfg::ROWS;
@@ -134,15 +172,19 @@ chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nslots, dou
     }
     __syncthreads();
 
-    for (int ms = blockIdx.x; ms < nslots; ms += gridDim.x) {
+    // a unit = one row, or one segment of DM_SEG stored entries of a long row (their partial tiles are summed by the factor kernel)
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        int ms, seg;
+        sp.locate(unit, ms, seg);
         const int row = p.plan.order[slot0 + ms];
-        const size_t beg = p.X.ptr[row];
-        const int nnz = (int)(p.X.ptr[row + 1] - beg);
-        if (nnz <= 0 && !(MODEL != kModelExplicit && p.solve_all_rows)) continue;   // the factor kernel deals with it
+        const size_t beg = p.X.ptr[row] + (size_t)seg * DM_SEG;
+        const int nnz_row = (int)(p.X.ptr[row + 1] - p.X.ptr[row]);
+        const int nnz = min(DM_SEG, nnz_row - seg * DM_SEG);
+        if (nnz_row <= 0 && !(MODEL != kModelExplicit && p.solve_all_rows)) continue;   // the factor kernel deals with it
         double lam = p.lam, lam_last = p.lam_last;
-        if (!IMPLICIT && p.scale_lam && nnz > 0) {
-            lam *= (double)nnz;
-            if (!p.scale_bias_const) lam_last *= (double)nnz;
+        if (!IMPLICIT && p.scale_lam && nnz_row > 0) {
+            lam *= (double)nnz_row;
+            if (!p.scale_bias_const) lam_last *= (double)nnz_row;
         }
 
         double acc[NTR + 1][2];
@@ -204,7 +246,8 @@ chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nslots, dou
         }
 
         // ---- 2. regulariser, constant matrix, per-row vector; tiles out as they sit in the accumulators
-        double *wm = ws + (size_t)ms * (Cfg::NTILES * 64);
+        double *wm = ws + (size_t)unit * (Cfg::NTILES * 64);
+        const bool lead = seg == 0;   // regulariser, constant matrix and per-row vector go to the first segment only
 #pragma unroll
         for (int s = 0; s <= NTR; s++) {
             const bool first = s < NTR && s <= r2;
@@ -215,6 +258,7 @@ chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nslots, dou
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int b = b0 + e;
+                    if (!lead) continue;
                     if (a < kd && b < kd) {
                         double v = acc[s][e];
                         if (MODEL != kModelExplicit && p.gram && a < kk && b < kk) v += __ldg(p.gram + (size_t)a * kk + b);
@@ -256,7 +300,7 @@ constexpr int DM_SCR = 160;         // doubles of shared scratch per warp
 
 template <int NTR, int MODEL>
 __global__ void __launch_bounds__(DM_FW * 32, DM_FMINB)
-chol_dmma_factor_kernel(const CgSweepParams p, int kd, int slot0, int nslots, double *ws)
+chol_dmma_factor_kernel(const CgSweepParams p, int kd, int slot0, int nslots, DmSplit sp, double *ws)
 {
     typedef DmCfg<NTR> Cfg;
     constexpr bool IMPLICIT = MODEL == kModelImplicit;
@@ -284,7 +328,9 @@ chol_dmma_factor_kernel(const CgSweepParams p, int kd, int slot0, int nslots, do
             }
             continue;
         }
-        double *wm = ws + (size_t)ms * (Cfg::NTILES * 64);
+        int u0, nseg;
+        sp.units_of(ms, u0, nseg);
+        double *wm = ws + (size_t)u0 * (Cfg::NTILES * 64);   // L overwrites the first unit's tiles
 
         for (int j = 0; j <= p_last; j++) {
             // ---- column j of the extended matrix
@@ -295,6 +341,11 @@ chol_dmma_factor_kernel(const CgSweepParams p, int kd, int slot0, int nslots, do
                     const double2 v = *reinterpret_cast<const double2 *>(wm + Cfg::tile_at(i, j) + 2 * lane);
                     t[i][0] = v.x;
                     t[i][1] = v.y;
+                    for (int sgm = 1; sgm < nseg; sgm++) {   // the partial tiles of a long row's other segments
+                        const double2 u = *reinterpret_cast<const double2 *>(wm + (size_t)sgm * (Cfg::NTILES * 64) + Cfg::tile_at(i, j) + 2 * lane);
+                        t[i][0] += u.x;
+                        t[i][1] += u.y;
+                    }
                 } else {
                     t[i][0] = t[i][1] = 0.0;
                 }
@@ -483,17 +534,57 @@ template <int NTR, int MODEL, int BPS> int launch_dmma(const CgSweepParams &p, i
     const int n = p.plan.n_rows;
     if (n < 1) return 0;
     const size_t per = (size_t)Cfg::NTILES * 64;
-    int batch = dmma_env("CMFB200_DMMA_BATCH", 16384);
-    if (batch > n) batch = n;
-    double *ws = dmma_workspace((size_t)batch * per);
-    if (!ws) return 1;
-    for (int s0 = 0; s0 < n; s0 += batch) {
-        const int ns = n - s0 < batch ? n - s0 : batch;
+    int batch = dmma_env("CMFB200_DMMA_BATCH", 16384);   // units per batch
+    if (batch < 64) batch = 64;
+    const int_t *deg = p.plan.host_deg;                  // descending; null: no splitting
+    const bool split_on = deg && dmma_env("CMFB200_DMMA_SPLIT", 0) != 0;   // measured: 32.7 ms with, 31.6 ms without at config 3 on one GPU (profiles/README.md)
+    static int *d_prefix[64] = {nullptr};
+    static int d_prefix_cap[64] = {0};
+    if (dev < 0 || dev >= 64) return 3;
+    std::vector<int> prefix;
+    int s0 = 0;
+    while (s0 < n) {
+        // rows [s0, s0 + ns): the leading long rows cut into units of DM_SEG entries, at most `batch` units in all
+        prefix.clear();
+        prefix.push_back(0);
+        int ns = 0, units = 0;
+        while (s0 + ns < n && split_on && deg[s0 + ns] > DM_SEG) {
+            const int u = (deg[s0 + ns] + DM_SEG - 1) / DM_SEG;
+            if (ns > 0 && units + u > batch) break;
+            units += u;
+            prefix.push_back(units);
+            ns++;
+        }
+        const int n_split = ns, units_split = units;
+        if (s0 + ns < n && !(split_on && deg[s0 + ns] > DM_SEG)) {
+            const int more = std::min(n - s0 - ns, std::max(0, batch - units));
+            ns += more;
+            units += more;
+        }
+        if (ns == 0) return 1;
+        double *ws = dmma_workspace((size_t)std::max(units, batch) * per);
+        if (!ws) return 1;
+        DmSplit sp{nullptr, n_split, units_split};
+        if (n_split > 0) {
+            if (d_prefix_cap[dev] < n_split + 1) {
+                if (d_prefix[dev]) cudaFree(d_prefix[dev]);
+                d_prefix[dev] = nullptr;
+                d_prefix_cap[dev] = 0;
+                if (cudaMalloc((void **)&d_prefix[dev], (size_t)(n_split + 1024) * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 1; }
+                d_prefix_cap[dev] = n_split + 1024;
+            }
+            // the host vector is reused by the next batch: the copy must have left it before that
+            if (cudaMemcpyAsync(d_prefix[dev], prefix.data(), (size_t)(n_split + 1) * sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+                cudaStreamSynchronize(stream) != cudaSuccess)
+                return 1;
+            sp.prefix = d_prefix[dev];
+        }
         long long gb = (long long)sms * occ, gf = (long long)sms * occf;
-        if (gb > ns) gb = ns;
+        if (gb > units) gb = units;
         if (gf > (ns + DM_FW - 1) / DM_FW) gf = (ns + DM_FW - 1) / DM_FW;
-        build<<<(unsigned)gb, Cfg::NT, smem, stream>>>(p, kd, s0, ns, ws);
-        factor<<<(unsigned)gf, DM_FW * 32, 0, stream>>>(p, kd, s0, ns, ws);
+        build<<<(unsigned)gb, Cfg::NT, smem, stream>>>(p, kd, s0, units, sp, ws);
+        factor<<<(unsigned)gf, DM_FW * 32, 0, stream>>>(p, kd, s0, ns, sp, ws);
+        s0 += ns;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
