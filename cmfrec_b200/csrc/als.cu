@@ -4,6 +4,7 @@
 #include "device_prep.h"
 #include "collective.h"
 #include "dense_small.h"
+#include <chrono>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -311,6 +312,16 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
         link = new NcclLink();
         if (link->init(nccl_id, cfg.rank, cfg.world) != 0) return 1;
     }
+    // CMFB200_TIMING=1: wall-clock of every ingestion stage to stderr (synchronises after each; a measurement aid)
+    const bool timing = std::getenv("CMFB200_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(stream);
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[cmfb200 timing]   ingest: %-34s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     // ---- the triplets on the device, centred / scaled
     DevBuf<int_t> dA, dB;
     DevBuf<real_t> dX;
@@ -327,11 +338,13 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
         }
         pA = dA.p; pB = dB.p; pX = dX.p;
     }
+    mark("allocate + upload COO");
     if (nnz) {
         if (mu_later) mu = (*mu_later)();   // computed on a host thread while the copies above were in flight
         if (mu != 0 && device_subtract(pX, nnz, mu, stream)) return 1;
         if (scale != 1) scale_kernel<real_t><<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(pX, nnz, scale);
     }
+    mark("wait for the mean, centre / scale");
     // ---- both orientations in full (caller numbering)
     if (!byA.ptr.alloc((size_t)cfg.m + 1) || !byA.idx.alloc(cap) || !byA.val.alloc(cap) || !byB.ptr.alloc((size_t)cfg.n + 1) ||
         !byB.idx.alloc(cap) || !byB.val.alloc(cap))
@@ -342,6 +355,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
     if (rc) return rc;
     launches += 12;
     dA.release(); dB.release(); dX.release();
+    mark("CSR + CSC");
     // ---- starting biases from the full matrices (caller numbering)
     DevBuf<real_t> bias_fullA, bias_fullB;
     if (!bias_fullA.alloc((size_t)cfg.m) || !bias_fullB.alloc((size_t)cfg.n)) return 1;
@@ -362,6 +376,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
         }
         if (rc) return rc;
     }
+    mark("starting biases");
     ldA = cmf_ld_for(cfg.kk);
     ldB = cmf_ld_for(cfg.kk);
     if (cfg.world == 1) {
@@ -399,6 +414,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
         launches += 10;
         if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;   // the full matrices are released on leaving this scope
     }
+    mark("row plan / dealing");
     if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB) ||
         !biasA.alloc(renA.rows_padded) || !biasB.alloc(renB.rows_padded))
         return 1;
@@ -426,6 +442,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
             values_positive = out == real_t(0);
         }
     }
+    mark("factor buffers");
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 

@@ -12,6 +12,7 @@
 #include "dense_small.h"
 #include "postfit.h"
 #include "nccl_link.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -48,7 +49,7 @@ int CollectiveState::setup(AlsState *state, const CollectiveConfig &c, const rea
     }
     const int pmax = std::max(std::max(cc.p, cc.q), k);
     if (!QA.alloc((size_t)k * k) || !QB.alloc((size_t)k * k) || !G1.alloc((size_t)k * k) || !G2.alloc((size_t)k * k) ||
-        !T1.alloc((size_t)pmax * k) || !Ldev.alloc((size_t)k * k) || !ws.alloc(xty_workspace_elems(pmax, k)) ||
+        !T1.alloc((size_t)pmax * k) || !Ldev.alloc((size_t)k * k) || !ws.alloc(std::max(xty_workspace_elems(pmax, k), gram_workspace_elems(k))) ||
         !qA.alloc(mp * ldq) || !qB.alloc(np_ * ldq))
         return 1;
     st->extra_ldq[0] = st->extra_ldq[1] = ldq;
@@ -60,7 +61,7 @@ int CollectiveState::update_side_factor(const real_t *F, int ldF, int_t rows, co
 {
     const int k = st->cfg.kk;
     cudaStream_t s = st->stream;
-    int rc = launch_xty(F, ldF, k, F, ldF, k, rows, G1.p, ws.p, s);
+    int rc = launch_gram(F, ldF, rows, k, G1.p, ws.p, s);   // F^T F (tcgen05 where gram_tc.cu covers the shape)
     if (rc) return rc;
     if ((rc = launch_xty(S, p, p, F, ldF, k, rows, T1.p, ws.p, s))) return rc;       // S^T F : [p x k]
     // each of the p rows of S^T F is a right-hand side of the k x k system (posv with p right-hand sides)
@@ -75,7 +76,7 @@ int CollectiveState::update_implicit_factor(const DeviceSide &side, const real_t
 {
     const int k = st->cfg.kk;
     cudaStream_t s = st->stream;
-    int rc = launch_xty(F, ldF, k, F, ldF, k, rowsF, G1.p, ws.p, s);
+    int rc = launch_gram(F, ldF, rowsF, k, G1.p, ws.p, s);
     if (rc) return rc;
     if ((rc = launch_spd_factor(G1.p, k, lam, Ldev.p, s))) return rc;
     if ((rc = launch_spmm_ones(side.view(), side.plan(), F, ldF, k, real_t(1), false, Out, k, s))) return rc;
@@ -100,8 +101,8 @@ int CollectiveState::build_extras(int which, const DeviceSide &side, int_t rows,
     const int ldq = st->extra_ldq[which];
     int rc = 0;
     const bool has_side = p > 0, has_imp = cc.implicit_features;
-    if (has_side && (rc = launch_xty(Cfac, k, k, Cfac, k, k, p, G1.p, ws.p, s))) return rc;
-    if (has_imp && (rc = launch_xty(Fi_opp, k, k, Fi_opp, k, k, rows_opp, G2.p, ws.p, s))) return rc;
+    if (has_side && (rc = launch_xty(Cfac, k, k, Cfac, k, k, p, G1.p, ws.p, s))) return rc;   // p rows only
+    if (has_imp && (rc = launch_gram(Fi_opp, k, rows_opp, k, G2.p, ws.p, s))) return rc;
     if ((rc = launch_axpby(k * k, w_side, has_side ? G1.p : nullptr, cc.w_implicit, has_imp ? G2.p : nullptr, Q, s))) return rc;
     bool acc = false;
     if (has_side) {

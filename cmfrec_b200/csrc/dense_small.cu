@@ -5,6 +5,7 @@
 #include "device_utils.cuh"
 #include <cstdint>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace cmfb200 {
@@ -176,6 +177,59 @@ __global__ void tri_solve_rows_kernel(const T *__restrict__ Lmat, int d, T *__re
             __syncwarp();
         }
         for (int i = lane; i < d; i += 32) x[i] = ys[i];
+        __syncwarp();
+    }
+}
+
+// The same solve with one LANE per row: a warp takes 32 rows, loads them coalesced and parks them transposed in shared
+// memory (ys[i][row], row stride 33: conflict-free both ways), then every lane runs the two substitutions of its own row
+// with the elements of L broadcast from shared memory -- no shuffles, no per-step synchronisation.  Used when L and the
+// parked rows fit shared memory (launch_tri_solve_rows picks the number of warps per block).
+template <typename T>
+__global__ void tri_solve_lanes_kernel(const T *__restrict__ Lmat, int d, T *__restrict__ R, int ldr, int_t rows)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Ls = reinterpret_cast<T *>(smem_raw);                  // [d][d+1]; the diagonal holds its reciprocal-free value
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *ys = Ls + (size_t)d * (d + 1) + (size_t)w * d * 33;    // [warps][d][33]
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) Ls[(i / d) * (d + 1) + (i % d)] = Lmat[i];
+    __syncthreads();
+    for (long long r0 = ((long long)blockIdx.x * warps + w) * 32; r0 < rows; r0 += (long long)gridDim.x * warps * 32) {
+        const int nr = rows - r0 < 32 ? (int)(rows - r0) : 32;
+        for (int rr = 0; rr < nr; rr++) {
+            const T *x = R + (size_t)(r0 + rr) * ldr;
+            for (int i = lane; i < d; i += 32) ys[i * 33 + rr] = x[i];
+        }
+        __syncwarp();
+        if (lane < nr) {
+            T *y = ys + lane;
+            for (int i = 0; i < d; i++) {                     // forward: L y = b
+                const T *Li = Ls + i * (d + 1);
+                T s0 = T(0), s1 = T(0);
+                int t = 0;
+                for (; t + 1 < i; t += 2) {
+                    s0 = fma(Li[t], y[t * 33], s0);
+                    s1 = fma(Li[t + 1], y[(t + 1) * 33], s1);
+                }
+                if (t < i) s0 = fma(Li[t], y[t * 33], s0);
+                y[i * 33] = (y[i * 33] - (s0 + s1)) / Li[i];
+            }
+            for (int i = d - 1; i >= 0; i--) {                // backward: L^T x = y
+                T s0 = T(0), s1 = T(0);
+                int t = i + 1;
+                for (; t + 1 < d; t += 2) {
+                    s0 = fma(Ls[t * (d + 1) + i], y[t * 33], s0);
+                    s1 = fma(Ls[(t + 1) * (d + 1) + i], y[(t + 1) * 33], s1);
+                }
+                if (t < d) s0 = fma(Ls[t * (d + 1) + i], y[t * 33], s0);
+                y[i * 33] = (y[i * 33] - (s0 + s1)) / Ls[i * (d + 1) + i];
+            }
+        }
+        __syncwarp();
+        for (int rr = 0; rr < nr; rr++) {
+            T *x = R + (size_t)(r0 + rr) * ldr;
+            for (int i = lane; i < d; i += 32) x[i] = ys[i * 33 + rr];
+        }
         __syncwarp();
     }
 }
@@ -422,6 +476,23 @@ int launch_spd_factor(const real_t *S_dev, int d, real_t lam, real_t *L_dev, cud
 int launch_tri_solve_rows(const real_t *L_dev, int d, real_t *R, int ldr, int_t rows, cudaStream_t stream)
 {
     if (rows < 1) return 0;
+    // many rows: one lane per row while L and 32 parked rows per warp fit shared memory
+    static const bool lanes_on = [] { const char *e = std::getenv("CMFB200_TRI_LANES"); return !e || std::atoi(e) != 0; }();
+    if (lanes_on && rows >= 256) {
+        for (int warps = 8; warps >= 2; warps >>= 1) {
+            const size_t smem = ((size_t)d * (d + 1) + (size_t)warps * d * 33) * sizeof(real_t);
+            const long long groups = ((long long)rows + 31) / 32;
+            if (smem > 200 * 1024 || (warps > 2 && (groups + warps - 1) / warps < sm_count())) continue;   // fill the SMs first
+            auto kern = tri_solve_lanes_kernel<real_t>;
+            if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                cudaGetLastError();
+                break;
+            }
+            const int blocks = (int)std::min<long long>((groups + warps - 1) / warps, 4LL * sm_count());
+            kern<<<blocks, warps * 32, smem, stream>>>(L_dev, d, R, ldr, rows);
+            return cudaGetLastError() == cudaSuccess ? 0 : 1;
+        }
+    }
     const int warps = 8;
     const size_t smem = ((size_t)d * (d + 1) + (size_t)warps * d) * sizeof(real_t);
     auto kern = tri_solve_rows_kernel<real_t>;

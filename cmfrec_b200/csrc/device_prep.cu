@@ -7,15 +7,25 @@
 //                        The integer outputs are identical to the reference's, entry for entry.
 //   centring             x - glob_mean in real_t                         src/common.c:3632-3644
 //   bias initialisation  initialize_biases_twosided / _onesided          src/common.c:4643-4669, 4799-4825, 4266-4289
-//                        one warp per row: coalesced fetch of 32 entries, then the reference's sequential chain
-//                        (running mean in double, residual formed in real_t) in its order, so results are bit-identical.
+//                        the reference's sequential chain (running mean in double, residual formed in real_t) in its
+//                        order, so results are bit-identical: one warp per short row, one block per long row with
+//                        producer warps feeding the chain through shared memory (bias_sweep_kernel).
 #include "device_prep.h"
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace cmfb200 {
 
 namespace {
+
+// NAME=0 in the environment switches an optional path off (a test and measurement aid)
+bool env_flag_off(const char *name)
+{
+    const char *e = std::getenv(name);
+    return e && std::atoi(e) == 0;
+}
 
 __global__ void iota_kernel(uint32_t *out, size_t n)
 {
@@ -58,25 +68,163 @@ template <typename T> __global__ void subtract_kernel(T *x, size_t n, T mu)
 }
 
 // one sweep of the bias initialisation over one orientation: bias[r] = shrunken running mean of (x - other[idx]).
-// One WARP per row: the lanes fetch 32 consecutive entries (coalesced values and indices, gathered biases), form the
-// residuals in real_t and the reciprocals of the running counts, and park them in shared memory; then every lane walks
-// the same sequential chain  mean += (resid - mean) / count  over the 32 parked entries in the reference's order, so
-// the result is bit-identical to the reference's scalar loop.  The division is the correctly rounded quotient from a
-// correctly rounded reciprocal (q0 = d * y, rem = fma(-q0, n, d) exact, q = fma(rem, y, q0): Markstein's final step,
-// exact for integer n), which keeps the IEEE division routine off the chain.
+// The running mean  mean += (resid - mean) / count  is a strictly sequential chain in the reference's order (the result
+// is bit-identical to the reference's scalar loop), so a sweep takes as long as the longest row's chain: five dependent
+// FP64 operations per stored entry.  The division is the correctly rounded quotient from a correctly rounded reciprocal
+// (q0 = d * y, rem = fma(-q0, n, d) exact, q = fma(rem, y, q0): Markstein's final step, exact for integer n), which
+// keeps the IEEE division routine off the chain.
+//
+// Two roles in one launch:
+//  * rows of fewer than kBiasLongMin entries: one WARP per row.  The lanes fetch 32 consecutive entries (coalesced values
+//    and indices, gathered biases), form the residuals in real_t and the reciprocals of the running counts, and park
+//    them in shared memory; then every lane walks the same chain over the 32 parked entries.
+//  * longer rows: one BLOCK per row (the first n_long_blocks blocks of the grid, which the hardware dispatches first).
+//    Warps 1..7 are producers: they turn tile t+1 of the row (kBiasTile entries) into (residual, reciprocal) pairs in
+//    shared memory while warp 0 walks the chain over tile t -- nothing but the five chain operations and broadcast
+//    shared-memory reads is left in the consumer's loop (the guard on the operand range is integer work on the
+//    exponent field).  Rows of at least kBiasHugeMin entries are taken first.
 constexpr int kBiasWarps = 8;
+constexpr int kBiasLongMin = 1024;
+constexpr int kBiasHugeMin = 8192;
+constexpr int kBiasProducers = (kBiasWarps - 1) * 32;
+constexpr int kBiasPerProducer = 4;
+constexpr int kBiasTile = kBiasProducers * kBiasPerProducer;   // 896 entries = 14 KB per buffer
+
+// rows with at least kBiasLongMin entries: the huge ones from the front of `list`, the others from its back;
+// count[0] / count[1] = how many of each
+__global__ void bias_long_rows_kernel(int_t rows, const size_t *__restrict__ ptr, int_t *__restrict__ list, int *__restrict__ count)
+{
+    const int_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const size_t len = ptr[r + 1] - ptr[r];
+    if (len >= (size_t)kBiasHugeMin) list[atomicAdd(&count[0], 1)] = r;
+    else if (len >= (size_t)kBiasLongMin) list[rows - 1 - atomicAdd(&count[1], 1)] = r;
+}
+
+// exponent field of d for the range guard; an exact zero is harmless and reads as 1023
+__device__ __forceinline__ int bias_guard_exponent(double d)
+{
+    const unsigned hi = (unsigned)__double2hiint(d) & 0x7fffffffu;
+    const unsigned lo = (unsigned)__double2loint(d);
+    return (hi | lo) == 0u ? 1023 : (int)(hi >> 20);
+}
+// operands for which the three-step quotient is not guaranteed exact (|d| below 2^-923 or above 2^917, denormals,
+// infinities, NaN: never seen on ratings) send the row to the IEEE division routine
+__device__ __forceinline__ bool bias_guard_suspicious(int emin, int emax) { return emin < 100 || emax > 1940; }
+
+template <typename T>
+__device__ __forceinline__ double bias_row_exact(size_t b, size_t e, const int_t *__restrict__ idx, const T *__restrict__ val,
+                                                 const T *__restrict__ other)
+{
+    double mean = 0.;
+    for (size_t t = b; t < e; t++) {
+        const T resid = other ? (T)(val[t] - other[idx[t]]) : val[t];
+        mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid, mean), (double)(t - b + 1)));
+    }
+    return mean;
+}
+
+template <typename T>
+__device__ __forceinline__ void bias_row_finish(int_t r, size_t cnt, double mean, T lam, bool scale_lam, bool clamp_count_to_one,
+                                                bool shrink_empty, T *__restrict__ out)
+{
+    if (cnt > 0 || shrink_empty) {
+        const double c = (double)cnt;
+        const double mult = scale_lam ? (clamp_count_to_one ? (double)(cnt > 1 ? cnt : 1) : c) : 1.;
+        mean = __dmul_rn(mean, __ddiv_rn(c, __dadd_rn(c, __dmul_rn((double)lam, mult))));
+    }
+    out[r] = (T)mean;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kBiasWarps * 32)
 bias_sweep_kernel(int_t rows, const size_t *__restrict__ ptr, const int_t *__restrict__ idx, const T *__restrict__ val,
                   const T *__restrict__ other, T lam, bool scale_lam, bool clamp_count_to_one, bool shrink_empty,
-                  T *__restrict__ out)
+                  T *__restrict__ out, const int_t *__restrict__ long_list, const int *__restrict__ long_count,
+                  int n_long_blocks)
 {
+    __shared__ double2 s_tile[2][kBiasTile];   // long rows: (residual, reciprocal of the running count)
     __shared__ double s_resid[kBiasWarps][32], s_rcp[kBiasWarps][32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int_t r = blockIdx.x * kBiasWarps + w;
+
+    if ((int)blockIdx.x < n_long_blocks) {
+        // ---------------------------------------------------------------- one block per long row
+        const int n_huge = long_count[0], n_all = n_huge + long_count[1];
+        for (int li = blockIdx.x; li < n_all; li += n_long_blocks) {
+            const int_t r = li < n_huge ? long_list[li] : long_list[rows - 1 - (li - n_huge)];
+            const size_t b = ptr[r], e = ptr[r + 1], len = e - b;
+            const int ntiles = (int)((len + kBiasTile - 1) / kBiasTile);
+            auto produce = [&](int t, int buf) {
+                const int pt = threadIdx.x - 32;
+                const size_t base = b + (size_t)t * kBiasTile;
+                int_t col[kBiasPerProducer];
+                T x[kBiasPerProducer], o[kBiasPerProducer];
+#pragma unroll
+                for (int j = 0; j < kBiasPerProducer; j++) {
+                    const size_t pos = base + j * kBiasProducers + pt;
+                    col[j] = 0;
+                    x[j] = T(0);
+                    if (pos < e) {
+                        x[j] = val[pos];
+                        if (other) col[j] = idx[pos];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kBiasPerProducer; j++) {
+                    const size_t pos = base + j * kBiasProducers + pt;
+                    o[j] = (other && pos < e) ? other[col[j]] : T(0);
+                }
+#pragma unroll
+                for (int j = 0; j < kBiasPerProducer; j++) {
+                    const size_t pos = base + j * kBiasProducers + pt;
+                    double2 v = make_double2(0., 0.);
+                    if (pos < e) {
+                        v.x = (double)(other ? (T)(x[j] - o[j]) : x[j]);
+                        v.y = __drcp_rn((double)(pos - b + 1));
+                    }
+                    s_tile[buf][j * kBiasProducers + pt] = v;
+                }
+            };
+            if (w > 0) produce(0, 0);
+            __syncthreads();
+            double mean = 0.;
+            int emin = 1023, emax = 1023;
+            for (int t = 0; t < ntiles; t++) {
+                if (w > 0) {
+                    if (t + 1 < ntiles) produce(t + 1, (t + 1) & 1);
+                } else {
+                    const size_t done = (size_t)t * kBiasTile;
+                    const int n = len - done < (size_t)kBiasTile ? (int)(len - done) : kBiasTile;
+                    const double2 *tile = s_tile[t & 1];
+                    double cnt = (double)done;
+#pragma unroll 8
+                    for (int u = 0; u < n; u++) {
+                        const double2 v = tile[u];
+                        cnt += 1.;
+                        const double d = __dsub_rn(v.x, mean);
+                        const double q0 = __dmul_rn(d, v.y);
+                        const double rem = __fma_rn(-q0, cnt, d);
+                        mean = __dadd_rn(mean, __fma_rn(rem, v.y, q0));
+                        const int ex = bias_guard_exponent(d);
+                        emin = min(emin, ex);
+                        emax = max(emax, ex);
+                    }
+                }
+                __syncthreads();
+            }
+            if (w == 0) {
+                if (bias_guard_suspicious(emin, emax)) mean = bias_row_exact(b, e, idx, val, other);   // warp-uniform
+                if (lane == 0) bias_row_finish(r, len, mean, lam, scale_lam, clamp_count_to_one, shrink_empty, out);
+            }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- one warp per short row
+    const int_t r = ((int_t)blockIdx.x - n_long_blocks) * kBiasWarps + w;
     if (r >= rows) return;
     const size_t b = ptr[r], e = ptr[r + 1];
+    if (n_long_blocks > 0 && e - b >= (size_t)kBiasLongMin) return;
     double mean = 0.;
     // this lane's entry of the 32-entry chunk starting at t0: residual (as the reference forms it, in real_t) and the
     // reciprocal of its running count
@@ -89,8 +237,8 @@ bias_sweep_kernel(int_t rows, const size_t *__restrict__ ptr, const int_t *__res
             rcp = __drcp_rn((double)(t - b + 1));
         }
     };
-    // the fetches run two chunks ahead of the chain: on the longest row the chain, not the memory latency, sets the pace
-    bool suspicious = false;
+    // the fetches run two chunks ahead of the chain
+    int emin = 1023, emax = 1023;
     double res1, rcp1, res2, rcp2;
     fetch(b, res1, rcp1);
     fetch(b + 32, res2, rcp2);
@@ -110,28 +258,15 @@ bias_sweep_kernel(int_t rows, const size_t *__restrict__ ptr, const int_t *__res
             const double q0 = __dmul_rn(d, y);
             const double rem = __fma_rn(-q0, cnt, d);
             mean = __dadd_rn(mean, __fma_rn(rem, y, q0));
-            // operands for which the three-step quotient is not guaranteed exact (never seen on ratings; checked off the
-            // chain: nothing below depends on it until the row is finished)
-            const double ad = fabs(d);
-            suspicious |= (ad != 0. && ad < 1e-280) || !(ad < 1e280);
+            const int ex = bias_guard_exponent(d);
+            emin = min(emin, ex);
+            emax = max(emax, ex);
         }
         __syncwarp();
     }
-    if (suspicious) {   // warp-uniform: every lane walked the same chain; redo the row with the IEEE division routine
-        mean = 0.;
-        for (size_t t = b; t < e; t++) {
-            const T resid = other ? (T)(val[t] - other[idx[t]]) : val[t];
-            mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn((double)resid, mean), (double)(t - b + 1)));
-        }
-    }
-    if (lane != 0) return;
-    const size_t cnt = e - b;
-    if (cnt > 0 || shrink_empty) {
-        const double c = (double)cnt;
-        const double mult = scale_lam ? (clamp_count_to_one ? (double)(cnt > 1 ? cnt : 1) : c) : 1.;
-        mean = __dmul_rn(mean, __ddiv_rn(c, __dadd_rn(c, __dmul_rn((double)lam, mult))));
-    }
-    out[r] = (T)mean;
+    // warp-uniform: every lane walked the same chain
+    if (bias_guard_suspicious(emin, emax)) mean = bias_row_exact(b, e, idx, val, other);
+    if (lane == 0) bias_row_finish(r, e - b, mean, lam, scale_lam, clamp_count_to_one, shrink_empty, out);
 }
 
 }  // namespace
@@ -381,20 +516,50 @@ int device_gather_rows_back(const real_t *src, int lds, int_t rows, int kk, cons
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// the long-row list of one orientation (see bias_sweep_kernel) and how many blocks take rows from it
+struct BiasLongRows {
+    DevBuf<int_t> list;
+    DevBuf<int> count;
+    int blocks = 0;
+    int build(int_t rows, const size_t *ptr, cudaStream_t stream)
+    {
+        blocks = 0;
+        if (rows < 1 || env_flag_off("CMFB200_BIAS_LONG")) return 0;
+        if (!list.alloc((size_t)rows) || !count.alloc(2)) return 1;
+        if (cudaMemsetAsync(count.p, 0, 2 * sizeof(int), stream) != cudaSuccess) return 1;
+        bias_long_rows_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(rows, ptr, list.p, count.p);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        blocks = std::min<long long>((long long)sms * 4, rows);
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
+};
+
+template <typename T>
+static void launch_bias_sweep(int_t rows, const size_t *ptr, const int_t *idx, const T *val, const T *other, T lam, bool scale_lam,
+                              bool clamp_count_to_one, bool shrink_empty, T *out, const BiasLongRows &lr, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned)lr.blocks + (unsigned)((rows + kBiasWarps - 1) / kBiasWarps);
+    bias_sweep_kernel<T><<<grid, kBiasWarps * 32, 0, stream>>>(rows, ptr, idx, val, other, lam, scale_lam, clamp_count_to_one,
+                                                               shrink_empty, out, lr.list.p, lr.count.p, lr.blocks);
+}
+
 int device_init_biases_twosided(int_t m, int_t n, const size_t *csr_p, const int_t *csr_i, const real_t *csr_v,
                                 const size_t *csc_p, const int_t *csc_i, const real_t *csc_v, real_t lam_user, real_t lam_item,
                                 bool scale_lam, real_t *d_biasA, real_t *d_biasB, cudaStream_t stream)
 {
     if (fabs((double)lam_user) < (double)CMF_EPS) lam_user = CMF_EPS;
     if (fabs((double)lam_item) < (double)CMF_EPS) lam_item = CMF_EPS;
-    cudaMemsetAsync(d_biasA, 0, (size_t)m * sizeof(real_t), stream);
-    cudaMemsetAsync(d_biasB, 0, (size_t)n * sizeof(real_t), stream);
+    if (cudaMemsetAsync(d_biasA, 0, (size_t)m * sizeof(real_t), stream) != cudaSuccess ||
+        cudaMemsetAsync(d_biasB, 0, (size_t)n * sizeof(real_t), stream) != cudaSuccess)
+        return 1;
+    BiasLongRows long_items, long_users;
+    if (long_items.build(n, csc_p, stream) || long_users.build(m, csr_p, stream)) return 1;
 
     for (int s = 0; s < 5; s++) {
-        bias_sweep_kernel<real_t><<<(n + kBiasWarps - 1) / kBiasWarps, kBiasWarps * 32, 0, stream>>>(n, csc_p, csc_i, csc_v, d_biasA, lam_item,
-                                                                                        scale_lam, true, true, d_biasB);
-        bias_sweep_kernel<real_t><<<(m + kBiasWarps - 1) / kBiasWarps, kBiasWarps * 32, 0, stream>>>(m, csr_p, csr_i, csr_v, d_biasB, lam_user,
-                                                                                        scale_lam, false, false, d_biasA);
+        launch_bias_sweep<real_t>(n, csc_p, csc_i, csc_v, d_biasA, lam_item, scale_lam, true, true, d_biasB, long_items, stream);
+        launch_bias_sweep<real_t>(m, csr_p, csr_i, csr_v, d_biasB, lam_user, scale_lam, false, false, d_biasA, long_users, stream);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -403,9 +568,9 @@ int device_init_biases_onesided(int_t rows, const size_t *ptr, const real_t *val
                                 cudaStream_t stream)
 {
     if (fabs((double)lam) < (double)CMF_EPS) lam = CMF_EPS;
-
-    bias_sweep_kernel<real_t><<<(rows + kBiasWarps - 1) / kBiasWarps, kBiasWarps * 32, 0, stream>>>(rows, ptr, nullptr, val, nullptr, lam,
-                                                                                       scale_lam, true, true, d_bias);
+    BiasLongRows lr;
+    if (lr.build(rows, ptr, stream)) return 1;
+    launch_bias_sweep<real_t>(rows, ptr, nullptr, val, nullptr, lam, scale_lam, true, true, d_bias, lr, stream);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -37,6 +37,42 @@ def test_initial_state_bit_exact(gpu_libs, dtype):
     assert np.array_equal(a["A"], b["A"]) and np.array_equal(a["B"], b["B"])
 
 
+def _coo_with_long_rows(dt, seed):
+    """Ratings with item rows of 9500 (several tiles of the block-per-row bias kernel, ragged last tile), 2000, 1024 and
+    1023 entries (either side of its row-length threshold) and a user row of 2900 entries, on a sparse background."""
+    rng = np.random.default_rng(seed)
+    m, n = 12000, 3000
+    pairs = set()
+    for item, cnt in ((0, 9500), (1, 2000), (2, 1024), (3, 1023)):
+        for u in rng.choice(m, size=cnt, replace=False):
+            pairs.add((int(u), item))
+    for i in 4 + rng.choice(n - 4, size=2900, replace=False):
+        pairs.add((0, int(i)))
+    bg_r = rng.integers(0, m, size=30000)
+    bg_c = rng.integers(4, n, size=30000)
+    pairs.update(zip(bg_r.tolist(), bg_c.tolist()))
+    rc = np.array(sorted(pairs), dtype=np.int64)
+    X = (rng.integers(1, 11, size=rc.shape[0]) * 0.5).astype(dt)
+    return rc[:, 0].astype(np.int32), rc[:, 1].astype(np.int32), X, m, n
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("biases", [(True, True), (True, False), (False, True)])
+def test_initial_biases_bit_exact_with_long_rows(gpu_libs, dtype, biases):
+    """The bias initialisation is a sequential chain per row (reference src/common.c:4643-4669, :4799-4825): rows long
+    enough for the block-per-row path of bias_sweep_kernel must come out bit for bit like the short ones."""
+    dt = np.dtype(dtype)
+    L, R = gpu_libs[dt], _ref(dt)
+    ixA, ixB, X, m, n = _coo_with_long_rows(dt, 11)
+    kw = dict(niter=0, nthreads=4, user_bias=biases[0], item_bias=biases[1], scale_lam=True, lam=0.05)
+    a = fit_explicit(L, dt, ixA, ixB, X, m, n, 8, **kw)
+    b = fit_explicit(R, dt, ixA, ixB, X, m, n, 8, **kw)
+    assert a["rc"] == 0 and b["rc"] == 0
+    for key in ("biasA", "biasB"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["glob_mean"] == b["glob_mean"]
+
+
 CASES_EXPLICIT = [
     dict(),                                                             # default: biases, centre, CG
     dict(finalize_chol=True),                                           # last iteration exact (CMF default)
