@@ -114,7 +114,7 @@ REFERENCE_ENTRY_POINTS = ("fit_collective_explicit_als", "fit_collective_implici
                           "precompute_collective_explicit", "precompute_collective_implicit")
 
 PRODUCT_ENTRY_POINTS = REFERENCE_ENTRY_POINTS + (
-    "cmfb200_real_name", "cmfb200_device_count", "cmfb200_random_init", "cmfb200_coo_to_csr_and_csc",
+    "cmfb200_real_name", "cmfb200_device_count", "cmfb200_random_init", "cmfb200_random_init_threads", "cmfb200_coo_to_csr_and_csc",
     "cmfb200_global_mean", "cmfb200_init_biases_twosided", "cmfb200_partition_rows", "cmfb200_nccl_unique_id", "cmfb200_als_create",
     "cmfb200_gram", "cmfb200_set_world", "cmfb200_trim_pool", "cmfb200_debug_poison_smem", "cmfb200_als_destroy", "cmfb200_als_set_factors", "cmfb200_als_get_factors", "cmfb200_als_half_sweep",
     "cmfb200_als_iterate", "cmfb200_als_timed_iterate", "cmfb200_als_set_profile",
@@ -185,6 +185,8 @@ def bind_product(lib, dtype):
     lib.cmfb200_device_count.argtypes = []
     lib.cmfb200_random_init.restype = None
     lib.cmfb200_random_init.argtypes = [P, c_size_t, P, c_size_t, c_int, c_bool]
+    lib.cmfb200_random_init_threads.restype = None
+    lib.cmfb200_random_init_threads.argtypes = [P, c_size_t, P, c_size_t, c_int, c_bool, c_int]
     lib.cmfb200_coo_to_csr_and_csc.restype = None
     lib.cmfb200_coo_to_csr_and_csc.argtypes = [P, P, P, c_int, c_int, c_size_t, P, P, P, P, P, P]
     lib.cmfb200_global_mean.restype = real

@@ -315,6 +315,11 @@ void cmfb200_random_init(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t
     random_init(A, sizeA, B, sizeB, seed, normal);
 }
 
+void cmfb200_random_init_threads(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal, int nthreads)
+{
+    random_init(A, sizeA, B, sizeB, seed, normal, nthreads);
+}
+
 void cmfb200_coo_to_csr_and_csc(const int_t *Xrow, const int_t *Xcol, const real_t *Xval, int_t m, int_t n, size_t nnz,
                                 size_t *csr_p, int_t *csr_i, real_t *csr_v, size_t *csc_p, int_t *csc_i, real_t *csc_v)
 {

@@ -133,7 +133,7 @@ int fit_explicit(const ExplicitArgs &a)
     const size_t sizeA = (size_t)m * kk, sizeB = (size_t)n * kk;
     const bool fill_B = a.II || a.add_implicit_features;   // src/collective.c:8243
     std::thread rng([&]() {
-        random_init(a.A, sizeA, fill_B ? a.B : nullptr, fill_B ? sizeB : 0, a.seed, true);
+        random_init(a.A, sizeA, fill_B ? a.B : nullptr, fill_B ? sizeB : 0, a.seed, true, a.nthreads);
         if (use_cg && !fill_B) std::memset(a.B, 0, sizeB * sizeof(real_t));
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
@@ -292,7 +292,7 @@ int fit_implicit(const ImplicitArgs &a)
     // starting point on a host thread: A uniform (normal for tiny problems), B zero with CG (src/collective.c:9750-9774)
     const bool fill_B = a.II != nullptr;   // src/collective.c:9752
     std::thread rng([&]() {
-        random_init(a.A, (size_t)m * kk, fill_B ? a.B : nullptr, fill_B ? (size_t)n * kk : 0, a.seed, false);
+        random_init(a.A, (size_t)m * kk, fill_B ? a.B : nullptr, fill_B ? (size_t)n * kk : 0, a.seed, false, a.nthreads);
         if (use_cg && !fill_B) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};

@@ -7,7 +7,7 @@ namespace cmfb200 {
 void seed_state(int_t seed, uint64_t state[4]);
 void fill_normal(real_t *out, size_t n, uint64_t state[4]);
 void fill_uniform(real_t *out, size_t n, uint64_t state[4]);
-void random_init(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal);
+void random_init(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal, int nthreads = 1);
 
 void coo_to_csr_and_csc(const int_t *row, const int_t *col, const real_t *val, int_t m, int_t n, size_t nnz,
                         size_t *csr_p, int_t *csr_i, real_t *csr_v, size_t *csc_p, int_t *csc_i, real_t *csc_v);

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 
 #ifndef CMF_TM_ENABLE
 #define CMF_TM_ENABLE 0   // tensor memory as a second cache tier: measured neutral (profiles/README.md), compiled out; make EXTRA=-DCMF_TM_ENABLE=1
@@ -606,10 +607,14 @@ struct SideStreams {
     }
 };
 
+// one set per calling host thread and device: concurrent fits from different host threads, or fits on several devices of
+// one process, never share streams or events (the sets live as long as their thread)
 SideStreams &side_streams()
 {
-    static SideStreams ss;   // one process drives one GPU
-    return ss;
+    thread_local std::map<int, SideStreams> per_device;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return per_device[dev];
 }
 
 // number of rows of the (descending) degree list with more than `x` stored entries

@@ -260,8 +260,8 @@ template <typename T> size_t chol_smem_bytes(int kd, int kdp, int ntile_rows, bo
 // per-device scratch for the MG variant, grown on demand and kept for the life of the process
 template <typename T> T *chol_workspace(size_t elems)
 {
-    static T *buf[64] = {nullptr};
-    static size_t cap[64] = {0};
+    thread_local T *buf[64] = {nullptr};   // per host thread: concurrent fits never share scratch
+    thread_local size_t cap[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;

@@ -179,7 +179,8 @@ chol_dmma_build_kernel(const CgSweepParams p, int kd, int slot0, int nunits, DmS
         const int row = p.plan.order[slot0 + ms];
         const size_t beg = p.X.ptr[row] + (size_t)seg * DM_SEG;
         const int nnz_row = (int)(p.X.ptr[row + 1] - p.X.ptr[row]);
-        const int nnz = min(DM_SEG, nnz_row - seg * DM_SEG);
+        // only the rows in front of the batch are cut into segments; every other row is one unit whatever its length
+        const int nnz = ms < sp.n_split ? min(DM_SEG, nnz_row - seg * DM_SEG) : nnz_row;
         if (nnz_row <= 0 && !(MODEL != kModelExplicit && p.solve_all_rows)) continue;   // the factor kernel deals with it
         double lam = p.lam, lam_last = p.lam_last;
         if (!IMPLICIT && p.scale_lam && nnz_row > 0) {
@@ -492,8 +493,8 @@ chol_dmma_factor_kernel(const CgSweepParams p, int kd, int slot0, int nslots, Dm
 // per-device tile workspace, grown on demand and kept for the life of the process
 double *dmma_workspace(size_t elems)
 {
-    static double *buf[64] = {nullptr};
-    static size_t cap[64] = {0};
+    thread_local double *buf[64] = {nullptr};   // per host thread: concurrent fits never share scratch
+    thread_local size_t cap[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
@@ -538,8 +539,8 @@ template <int NTR, int MODEL, int BPS> int launch_dmma(const CgSweepParams &p, i
     if (batch < 64) batch = 64;
     const int_t *deg = p.plan.host_deg;                  // descending; null: no splitting
     const bool split_on = deg && dmma_env("CMFB200_DMMA_SPLIT", 0) != 0;   // measured: 32.7 ms with, 31.6 ms without at config 3 on one GPU (profiles/README.md)
-    static int *d_prefix[64] = {nullptr};
-    static int d_prefix_cap[64] = {0};
+    thread_local int *d_prefix[64] = {nullptr};
+    thread_local int d_prefix_cap[64] = {0};
     if (dev < 0 || dev >= 64) return 3;
     std::vector<int> prefix;
     int s0 = 0;

@@ -305,6 +305,9 @@ int cmfb200_device_count(void);
 /* --- host-side preparation, bit-exact counterparts of reference helpers --------------------------------- */
 /* random_parallel, reference src/helpers.c:930-1043 (A from the seed state, B from the jumped state) */
 void cmfb200_random_init(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal);
+/* the same matrices filled by `nthreads` threads (what the fits call): the generator is jumped to the start of every
+ * 2^15-draw chunk, the chunks are sampled independently and stitched in order -- values identical to the call above */
+void cmfb200_random_init_threads(real_t *A, size_t sizeA, real_t *B, size_t sizeB, int_t seed, bool normal, int nthreads);
 /* coo_to_csr_and_csc, reference src/helpers.c:1375-1491 (no weights) */
 void cmfb200_coo_to_csr_and_csc(const int_t *Xrow, const int_t *Xcol, const real_t *Xval, int_t m, int_t n, size_t nnz,
                                 size_t *csr_p, int_t *csr_i, real_t *csr_v,

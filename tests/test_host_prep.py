@@ -84,3 +84,35 @@ def test_against_reference_build(dtype):
         R.random_parallel(ArraysToFill(ptr(A1), sa, ptr(B1) if sb else None, sb), seed, normal, 4)
         L.cmfb200_random_init(ptr(A2), sa, ptr(B2) if sb else None, sb, seed, normal)
         assert np.array_equal(A1, A2) and np.array_equal(B1, B2), (sa, sb, normal, seed)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_threaded_random_init_is_the_sequential_one(dtype):
+    """cmfb200_random_init_threads (what the fits call): the generator jumped to every 2^15-draw chunk, chunks sampled
+    independently for both ways of entering them and stitched in order -- must reproduce the sequential streams of
+    reference random_parallel (src/helpers.c:930-1043) bit for bit, for the ziggurat (variable draws per sample) and
+    the uniform sampler (odd-length quirk included), whatever the number of threads."""
+    dt = np.dtype(dtype)
+    L = _lib.load(dt)
+    cases = [(1500007, 0, True, 1), (300000, 700001, True, -5), (300001, 0, False, 7), (2**18 + 5, 3, False, 0),
+             (2**17 * 4, 2**17 * 4 + 1, True, 5), (1000003, 500001, False, 123), (1000, 500, True, 9)]
+    for sa, sb, normal, seed in cases:
+        A1 = np.full(sa, -7, dt); B1 = np.full(max(sb, 1), -7, dt)
+        L.cmfb200_random_init(ptr(A1), sa, ptr(B1) if sb else None, sb, seed, normal)
+        for nt in (2, 3, 8):
+            A2 = np.full(sa, -7, dt); B2 = np.full(max(sb, 1), -7, dt)
+            L.cmfb200_random_init_threads(ptr(A2), sa, ptr(B2) if sb else None, sb, seed, normal, nt)
+            assert np.array_equal(A1, A2) and np.array_equal(B1, B2), (sa, sb, normal, seed, nt)
+
+
+def test_threaded_random_init_in_several_rounds(monkeypatch):
+    """The ziggurat fill guesses how many chunks of draws it needs; when the guess falls short it goes on from where it
+    stopped (state and entry carried over).  CMFB200_RNG_TIGHT makes every round fall short."""
+    dt = np.dtype(np.float32)
+    L = _lib.load(dt)
+    sa = 1500007
+    A1 = np.zeros(sa, dt); A2 = np.zeros(sa, dt)
+    L.cmfb200_random_init(ptr(A1), sa, None, 0, 3, True)
+    monkeypatch.setenv("CMFB200_RNG_TIGHT", "1")
+    L.cmfb200_random_init_threads(ptr(A2), sa, None, 0, 3, True, 4)
+    assert np.array_equal(A1, A2)
