@@ -179,7 +179,7 @@ class ClockSampler:
 def time_reference(w, data, steps, warmup, nthreads):
     """The reference's own CPU implementation of the same fit: sec / iteration = (t(K iters) - t(0 iters)) / K."""
     import refload
-    from support import fit_explicit, fit_implicit
+    from cmfrec_b200.calls import fit_explicit, fit_implicit
     a, b, x, m, n, dt = data
     R = refload.ref(dt)
     kind = "reference"
@@ -406,8 +406,7 @@ def main():
     import torch
     import torch.distributed as dist
     from cmfrec_b200 import _lib
-    from support import csr_csc, fit_explicit, fit_implicit
-    from refload import ptr
+    from cmfrec_b200.calls import csr_csc, fit_explicit, fit_implicit, ptr
 
     torch.cuda.set_device(local_rank)
     if world > 1:

@@ -538,7 +538,7 @@ template <int NTR, int MODEL, int BPS> int launch_dmma(const CgSweepParams &p, i
     int batch = dmma_env("CMFB200_DMMA_BATCH", 16384);   // units per batch
     if (batch < 64) batch = 64;
     const int_t *deg = p.plan.host_deg;                  // descending; null: no splitting
-    const bool split_on = deg && dmma_env("CMFB200_DMMA_SPLIT", 0) != 0;   // measured: 32.7 ms with, 31.6 ms without at config 3 on one GPU (profiles/README.md)
+    const bool split_on = deg && dmma_env("CMFB200_DMMA_SPLIT", 1) != 0;   // config 3 on one GPU: 32.6 ms with, 36.9 ms without (profiles/README.md)
     thread_local int *d_prefix[64] = {nullptr};
     thread_local int d_prefix_cap[64] = {0};
     if (dev < 0 || dev >= 64) return 3;
