@@ -265,6 +265,39 @@ template <typename T> __global__ void __launch_bounds__(256) spd_factor_kernel(c
     }
 }
 
+// The same factorisation (same operations on every element in the same order: identical results) with the matrix in shared
+// memory, row stride d + 1 (column accesses conflict-free); the working copy in global memory cost 87 us at d = 64.
+template <typename T> __global__ void __launch_bounds__(256) spd_factor_smem_kernel(const T *__restrict__ S, int d, T lam, T *__restrict__ Lout)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *W = reinterpret_cast<T *>(smem_raw);   // [d][d + 1]
+    __shared__ T dj_s;
+    const int tid = threadIdx.x, nt = blockDim.x, ld = d + 1;
+    for (int i = tid; i < d * d; i += nt) {
+        const int r = i / d, c = i % d;
+        W[r * ld + c] = (c <= r) ? S[i] + ((c == r) ? lam : T(0)) : T(0);
+    }
+    __syncthreads();
+    for (int j = 0; j < d; j++) {
+        if (tid == 0) {
+            const T v = sqrt(W[j * ld + j]);
+            W[j * ld + j] = v;
+            dj_s = v;
+        }
+        __syncthreads();
+        const T inv = T(1) / dj_s;
+        for (int i = j + 1 + tid; i < d; i += nt) W[i * ld + j] *= inv;
+        __syncthreads();
+        const int rem = d - j - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+            if (c <= i) W[i * ld + c] = fma(-W[i * ld + j], W[c * ld + j], W[i * ld + c]);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < d * d; i += nt) Lout[i] = W[(i / d) * ld + (i % d)];
+}
+
 template <typename T> __global__ void axpby_kernel(int n, T alpha, const T *x, T beta, const T *y, T *out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -469,6 +502,15 @@ int spd_factor_host(int d, const real_t *S_host, std::vector<real_t> &L_host)
 
 int launch_spd_factor(const real_t *S_dev, int d, real_t lam, real_t *L_dev, cudaStream_t stream)
 {
+    const size_t smem = (size_t)d * (d + 1) * sizeof(real_t);
+    if (smem <= 200 * 1024) {
+        auto kern = spd_factor_smem_kernel<real_t>;
+        if (smem <= 48 * 1024 || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+            kern<<<1, 256, smem, stream>>>(S_dev, d, lam, L_dev);
+            return cudaGetLastError() == cudaSuccess ? 0 : 1;
+        }
+        cudaGetLastError();
+    }
     spd_factor_kernel<real_t><<<1, 256, 0, stream>>>(S_dev, d, lam, L_dev);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
