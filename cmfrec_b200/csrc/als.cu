@@ -151,13 +151,13 @@ static int build_side(const size_t *ptr, const int_t *idx, const real_t *val, co
     if (!side.ptr.alloc(hptr.size()) || !side.idx.alloc(std::max<size_t>(total, 1)) ||
         !side.val.alloc(std::max<size_t>(total, 1)) || !side.order.alloc(std::max<size_t>(order.size(), 1)))
         return 1;
-    cudaMemcpyAsync(side.ptr.p, hptr.data(), hptr.size() * sizeof(size_t), cudaMemcpyHostToDevice, stream);
+    if (cudaMemcpyAsync(side.ptr.p, hptr.data(), hptr.size() * sizeof(size_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
     if (total) {
-        cudaMemcpyAsync(side.idx.p, hidx.data(), total * sizeof(int_t), cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(side.val.p, hval.data(), total * sizeof(real_t), cudaMemcpyHostToDevice, stream);
+        if (cudaMemcpyAsync(side.idx.p, hidx.data(), total * sizeof(int_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
+        if (cudaMemcpyAsync(side.val.p, hval.data(), total * sizeof(real_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
     }
     if (!order.empty())
-        cudaMemcpyAsync(side.order.p, order.data(), order.size() * sizeof(int_t), cudaMemcpyHostToDevice, stream);
+        if (cudaMemcpyAsync(side.order.p, order.data(), order.size() * sizeof(int_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
 }
 
@@ -225,10 +225,10 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB) ||
         !biasA.alloc(renA.rows_padded) || !biasB.alloc(renB.rows_padded))
         return 1;
-    cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream);
-    cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream);
-    cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream);
-    cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream);
+    if (cudaMemsetAsync(A.p, 0, A.n * sizeof(real_t), stream) != cudaSuccess) return 1;
+    if (cudaMemsetAsync(B.p, 0, B.n * sizeof(real_t), stream) != cudaSuccess) return 1;
+    if (cudaMemsetAsync(biasA.p, 0, biasA.n * sizeof(real_t), stream) != cudaSuccess) return 1;
+    if (cudaMemsetAsync(biasB.p, 0, biasB.n * sizeof(real_t), stream) != cudaSuccess) return 1;
     if (cfg.implicit) {
         if (!gram.alloc((size_t)cfg.kk * cfg.kk) || !gram_ws.alloc(gram_workspace_elems(cfg.kk))) return 1;
         if (device_all_positive(byA.val.p, byA.nnz_local, &values_positive, stream)) return 1;

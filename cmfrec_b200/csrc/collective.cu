@@ -34,18 +34,18 @@ int CollectiveState::setup(AlsState *state, const CollectiveConfig &c, const rea
     const size_t mp = (size_t)st->renA.rows_padded, np_ = (size_t)st->renB.rows_padded;
     if (cc.p > 0) {
         if (!Uc.alloc((size_t)m * cc.p) || !C.alloc((size_t)cc.p * k)) return 1;
-        cudaMemcpyAsync(Uc.p, Uc_host, Uc.n * sizeof(real_t), cudaMemcpyHostToDevice, s);
-        cudaMemsetAsync(C.p, 0, C.n * sizeof(real_t), s);
+        if (cudaMemcpyAsync(Uc.p, Uc_host, Uc.n * sizeof(real_t), cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+        if (cudaMemsetAsync(C.p, 0, C.n * sizeof(real_t), s) != cudaSuccess) return 1;
     }
     if (cc.q > 0) {
         if (!Ic.alloc((size_t)n * cc.q) || !D.alloc((size_t)cc.q * k)) return 1;
-        cudaMemcpyAsync(Ic.p, Ic_host, Ic.n * sizeof(real_t), cudaMemcpyHostToDevice, s);
-        cudaMemsetAsync(D.p, 0, D.n * sizeof(real_t), s);
+        if (cudaMemcpyAsync(Ic.p, Ic_host, Ic.n * sizeof(real_t), cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+        if (cudaMemsetAsync(D.p, 0, D.n * sizeof(real_t), s) != cudaSuccess) return 1;
     }
     if (cc.implicit_features) {
         if (!Ai.alloc(mp * k) || !Bi.alloc(np_ * k)) return 1;
-        cudaMemsetAsync(Ai.p, 0, Ai.n * sizeof(real_t), s);
-        cudaMemsetAsync(Bi.p, 0, Bi.n * sizeof(real_t), s);
+        if (cudaMemsetAsync(Ai.p, 0, Ai.n * sizeof(real_t), s) != cudaSuccess) return 1;
+        if (cudaMemsetAsync(Bi.p, 0, Bi.n * sizeof(real_t), s) != cudaSuccess) return 1;
     }
     const int pmax = std::max(std::max(cc.p, cc.q), k);
     if (!QA.alloc((size_t)k * k) || !QB.alloc((size_t)k * k) || !G1.alloc((size_t)k * k) || !G2.alloc((size_t)k * k) ||
