@@ -596,18 +596,20 @@ def main():
             # (CSR / CSC, centring, biases), the dealing of the rows to the ranks, K iterations with their all-gathers and
             # the download are all inside the timed region
             assert not w.get("side")
+            # host threads per rank: the ranks share the box's cores; at least 8, the reference's threshold for its parallel mean
+            nthr = max(8, ncpu // world)
             pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()
             pa, pb, px = pin(a), pin(b), pin(x)
             outbuf = dict(A=pin(np.zeros((m, w["k"]), dt)), B=pin(np.zeros((n, w["k"]), dt)))
             if w["implicit"]:
                 run = lambda nit: fit_implicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], alpha=h["alpha"], niter=nit,
-                                               use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
+                                               use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthr,
                                                copy_inputs=False, out=outbuf)
             else:
                 outbuf.update(biasA=pin(np.zeros(m, dt)), biasB=pin(np.zeros(n, dt)))
                 extra = dict(add_implicit_features=bool(w.get("implicit_features")), w_implicit=w.get("w_implicit", 1.0))
                 run = lambda nit: fit_explicit(L, dt, pa, pb, px, m, n, w["k"], lam=h["lam"], scale_lam=h["scale_lam"],
-                                               niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=ncpu,
+                                               niter=nit, use_cg=w["use_cg"], max_cg_steps=h["max_cg_steps"], nthreads=nthr,
                                                copy_inputs=False, out=outbuf, **extra)
             fresh_nccl_id()
             assert L.cmfb200_set_world(rank, world, opt.nccl_id) == 0

@@ -11,6 +11,7 @@
 #include "host_prep.h"
 #include "postfit.h"
 #include "collective.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -65,6 +66,16 @@ struct InterruptScope {
         if (installed) sigaction(SIGINT, &old_action, nullptr);
     }
 };
+
+// host threads for the starting factors: what the caller allows, within this process's share of the cores when several
+// ranks drive several GPUs of one box
+static int rng_threads(int nthreads)
+{
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int world = std::max(1, world_setting().world);
+    const int share = hw > 0 ? std::max(1, hw / world) : nthreads;
+    return std::max(1, std::min(nthreads, share));
+}
 
 static int refuse(const char *what)
 {
@@ -133,7 +144,7 @@ int fit_explicit(const ExplicitArgs &a)
     const size_t sizeA = (size_t)m * kk, sizeB = (size_t)n * kk;
     const bool fill_B = a.II || a.add_implicit_features;   // src/collective.c:8243
     std::thread rng([&]() {
-        random_init(a.A, sizeA, fill_B ? a.B : nullptr, fill_B ? sizeB : 0, a.seed, true, a.nthreads);
+        random_init(a.A, sizeA, fill_B ? a.B : nullptr, fill_B ? sizeB : 0, a.seed, true, rng_threads(a.nthreads));
         if (use_cg && !fill_B) std::memset(a.B, 0, sizeB * sizeof(real_t));
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
@@ -292,7 +303,7 @@ int fit_implicit(const ImplicitArgs &a)
     // starting point on a host thread: A uniform (normal for tiny problems), B zero with CG (src/collective.c:9750-9774)
     const bool fill_B = a.II != nullptr;   // src/collective.c:9752
     std::thread rng([&]() {
-        random_init(a.A, (size_t)m * kk, fill_B ? a.B : nullptr, fill_B ? (size_t)n * kk : 0, a.seed, false, a.nthreads);
+        random_init(a.A, (size_t)m * kk, fill_B ? a.B : nullptr, fill_B ? (size_t)n * kk : 0, a.seed, false, rng_threads(a.nthreads));
         if (use_cg && !fill_B) std::memset(a.B, 0, (size_t)n * kk * sizeof(real_t));
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{rng};
