@@ -220,6 +220,7 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
     if (rc) return rc;
     rc = build_side(csc_p, csc_i, csc_v, renB, renA, cfg.rank, stream, byB);
     if (rc) return rc;
+    if ((rc = prepare_hot())) return rc;
     ldA = cmf_ld_for(cfg.kk);
     ldB = cmf_ld_for(cfg.kk);
     if (!A.alloc((size_t)renA.rows_padded * ldA) || !B.alloc((size_t)renB.rows_padded * ldB) ||
@@ -234,6 +235,57 @@ int AlsState::setup(const AlsConfig &c, const size_t *csr_p, const int_t *csr_i,
         if (device_all_positive(byA.val.p, byA.nnz_local, &values_positive, stream)) return 1;
     }
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : 1;
+}
+
+// ---- hot opposing rows (sweep.h: CgSweepParams::hot_idx)
+namespace {
+__global__ void hot_slot_kernel(const int_t *__restrict__ hot_rows, int n_hot, int_t *__restrict__ slot1)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_hot) slot1[hot_rows[s]] = s + 1;
+}
+__global__ void hot_pack_kernel(const int_t *__restrict__ idx, size_t nnz, const int_t *__restrict__ slot1, int_t *__restrict__ out)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) {
+        const int_t col = idx[e];
+        out[e] = col | (slot1[col] << 20);
+    }
+}
+}  // namespace
+
+// The rows of one side that most stored entries of the other side point at (its first rows in degree order) are worth a
+// shared-memory table in the CG sweep over the other side when they cover a good share of all entries (item popularity is
+// heavy-tailed).  One GPU, fp32, 32 < k <= 128.  Opt-in (CMFB200_RES_HOT=1 on a build with -DCMF_RES_HOT_ENABLE): at ML10M
+// shape the 256 most popular items hold 19 % of the entries and the table loses (sweep_cg_resident.cu: kHotCompiled).
+static int prepare_hot_side(DeviceSide &side, const DeviceSide &opp, int_t opp_rows, int kk, cudaStream_t stream)
+{
+    side.n_hot = 0;
+    if (sizeof(real_t) != 4 || kk <= 32 || kk > 128 || env_or("CMFB200_RES_HOT", 0) == 0) return 0;   // opt-in, see sweep_cg_resident.cu
+    if (opp_rows >= (1 << 20) || opp.deg_sorted.empty() || side.nnz_local == 0) return 0;
+    int n_hot = env_or("CMFB200_RES_HOT_ROWS", kk <= 64 ? 256 : 128);
+    n_hot = std::min<long long>(std::min(n_hot, 2047), (long long)opp.deg_sorted.size());
+    if (n_hot < 1) return 0;
+    size_t covered = 0;
+    for (int i = 0; i < n_hot; i++) covered += (size_t)opp.deg_sorted[(size_t)i];
+    if (covered * 100 < side.nnz_local * (size_t)env_or("CMFB200_RES_HOT_MINPCT", 25)) return 0;
+    DevBuf<int_t> slot1;
+    if (!slot1.alloc((size_t)opp_rows) || !side.hot_rows.alloc((size_t)n_hot) || !side.hot_idx.alloc(side.nnz_local)) return 1;
+    if (cudaMemsetAsync(slot1.p, 0, (size_t)opp_rows * sizeof(int_t), stream) != cudaSuccess ||
+        cudaMemcpyAsync(side.hot_rows.p, opp.order.p, (size_t)n_hot * sizeof(int_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+        return 1;
+    hot_slot_kernel<<<(n_hot + 255) / 256, 256, 0, stream>>>(side.hot_rows.p, n_hot, slot1.p);
+    hot_pack_kernel<<<(unsigned)((side.nnz_local + 255) / 256), 256, 0, stream>>>(side.idx.p, side.nnz_local, slot1.p, side.hot_idx.p);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return 1;   // slot1 is released on return
+    side.n_hot = n_hot;
+    return 0;
+}
+
+int AlsState::prepare_hot()
+{
+    if (cfg.world > 1) return 0;   // the dealt numbering of several ranks is not handled yet
+    if (int rc = prepare_hot_side(byA, byB, cfg.n, cfg.kk, stream)) return rc;
+    return prepare_hot_side(byB, byA, cfg.m, cfg.kk, stream);
 }
 
 // bucket boundaries of a side from its (descending) degree list
@@ -384,6 +436,7 @@ int AlsState::setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *
         build_renumbering(nullptr, cfg.n, 1, renB);
         if ((rc = plan_side_from_device(byA, cfg.m, stream))) return rc;
         if ((rc = plan_side_from_device(byB, cfg.n, stream))) return rc;
+        if ((rc = prepare_hot())) return rc;
     } else {
         // ---- deal the rows to the ranks and keep this rank's blocks
         DeviceSide fullA, fullB;
@@ -561,6 +614,9 @@ int AlsState::half_sweep(int which, int iter, int solver)
     const DeviceSide &side = solveA ? byA : byB;
     p.X = side.view();
     p.plan = side.plan();
+    p.hot_idx = side.n_hot > 0 ? side.hot_idx.p : nullptr;
+    p.hot_rows = side.hot_rows.p;
+    p.n_hot = side.n_hot;
     p.lam = solveA ? cfg.lam_A : cfg.lam_B;
     p.lam_last = solveA ? cfg.lam_biasA : cfg.lam_biasB;
     p.scale_lam = cfg.scale_lam;

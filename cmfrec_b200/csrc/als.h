@@ -79,6 +79,10 @@ struct DeviceSide {
     DevBuf<int_t> order;
     std::vector<int_t> deg_sorted;   // host: stored entries of order[i], descending
     int_t n_order = 0, n_long = 0, n_huge = 0;
+    // CG sweeps over this side: the most gathered rows of the OPPOSING side kept in shared memory (AlsState::prepare_hot)
+    DevBuf<int_t> hot_idx;           // idx with the table slot + 1 packed into bits 20..30
+    DevBuf<int_t> hot_rows;          // the opposing rows in the table
+    int n_hot = 0;
     CsrView view() const { return CsrView{ptr.p, idx.p, val.p}; }
     SweepPlan plan() const { return SweepPlan{order.p, n_order, n_long, n_huge, deg_sorted.empty() ? nullptr : deg_sorted.data()}; }
 };
@@ -166,6 +170,7 @@ public:
     // built in full on every device, the rows are dealt to the ranks there (decreasing degree, round-robin) and only this
     // rank's blocks are kept.  coo_on_device: ixA / ixB / X are device pointers already.  bias: starting biases computed
     // on the device from the full matrices (before the dealing) and stored in device numbering.
+    int prepare_hot();   // after both sides are planned (one GPU): see DeviceSide::hot_idx
     int setup_from_coo(const AlsConfig &c, const int_t *ixA, const int_t *ixB, const real_t *X, size_t nnz, real_t mu,
                        real_t scale, cudaStream_t s, const std::function<real_t()> *mu_later = nullptr,   // mu_later: the mean is still being computed on the host; asked for once the uploads are in flight
                        const void *nccl_id = nullptr, const BiasInit *bias = nullptr, bool coo_on_device = false);

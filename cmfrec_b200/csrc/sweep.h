@@ -48,6 +48,12 @@ struct CgSweepParams {
     bool values_positive;         // implicit model: every stored value is > 0 (lets the tensor-core sweep use sqrt(x) weights)
     void *debug;                  // developer builds (-DNM_TIMING): device buffer for per-role cycle counts, else null
     cudaStream_t side_stream;     // optional second stream for the long-row kernel (caller orders it around the sweep)
+    // CG sweeps, optional: the n_hot most gathered opposing rows (hot_rows, device) are kept in a shared-memory table by
+    // every thread block; hot_idx = X.idx with the table slot + 1 packed into bits 20..30 (needs fewer than 2^20 opposing
+    // rows and n_hot <= 2047).  Null: every gather goes to L2.
+    const int_t *hot_idx;
+    const int_t *hot_rows;
+    int n_hot;
 };
 
 // returns 0, or 2 when kk is outside the supported range

@@ -88,7 +88,13 @@ constexpr int kTmemColsPerWarp = 128;    // warps w and w + 4 share a lane quart
 // Gather policy: this warp's entries come from its shared-memory region (first `cap` of them) or from L2
 // ---------------------------------------------------------------------------------------------------------
 // STREAM = false compiles the L2 path out (teams whose rows always fit)
-template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
+// HOT: the opposing rows that most entries point at (the first p.n_hot rows of the opposing side's degree order) sit in a
+// block-wide shared-memory table; p.hot_idx carries, per stored entry, the column with the table slot + 1 packed into bits
+// 20..30 (0 = not in the table), and the streamed gathers read such rows from the table instead of L2 (one generic load
+// serves both address spaces, so the pipeline of the streamed part is unchanged)
+constexpr int kHotShift = 20;
+constexpr int kHotColMask = (1 << kHotShift) - 1;
+template <typename T, int C, int L, bool STREAM = true, bool HOT = false> struct ResidentGather {
     typedef Layout<T, C, L> Lay;
     typedef typename VecOf<T>::type Vec;
     static constexpr int G = 32 / L;
@@ -120,6 +126,7 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
     static constexpr int TM_CHUNK_COLS = L * 8;   // a chunk is L steps of 8 columns
     uint32_t tm_addr = 0;
     int tm_chunks = 0;
+    const T *hot = nullptr;   // HOT: the table, [p.n_hot][KP]
 
     __device__ __forceinline__ ResidentGather(const CgSweepParams &p_, T *region, int cap_, int gw_, int GW_)
         : p(p_), rows(region), xs(region + (size_t)cap_ * RS), cap(cap_), beg(0), nnz(0), gw(gw_), GW(GW_)
@@ -225,6 +232,24 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
         x = __shfl_sync(CMF_FULL_MASK, x_r, ent);
         const bool ok = col >= 0;
         one = ok ? T(1) : T(0);
+        if constexpr (HOT) {
+            const int slot1 = ok ? (col >> kHotShift) : 0;
+            const T *grow = slot1 ? hot + (size_t)(slot1 - 1) * KP + l * VN
+                                  : p.G + (size_t)(ok ? (col & kHotColMask) : 0) * (size_t)p.ldG + l * VN;
+#pragma unroll
+            for (int q = 0; q < C / VN; q++) {
+                if (FULLW || slot1 || (q * L + l) * VN < p.ldG) {
+                    const Vec vv = *reinterpret_cast<const Vec *>(grow + q * L * VN);   // generic: shared or global
+                    const T *pv = reinterpret_cast<const T *>(&vv);
+#pragma unroll
+                    for (int e2 = 0; e2 < VN; e2++) v[q * VN + e2] = pv[e2];
+                } else {
+#pragma unroll
+                    for (int e2 = 0; e2 < VN; e2++) v[q * VN + e2] = T(0);
+                }
+            }
+            return;
+        }
         const T *grow = p.G + (size_t)(ok ? col : 0) * (size_t)p.ldG + l * VN;
 #pragma unroll
         for (int q = 0; q < C / VN; q++) {
@@ -255,9 +280,9 @@ template <typename T, int C, int L, bool STREAM = true> struct ResidentGather {
         col_r = -1;
         x_r = T(0);
         if (e < nnz) {
-            col_r = p.X.idx[beg + e];
+            col_r = HOT ? p.hot_idx[beg + e] : p.X.idx[beg + e];
             x_r = p.X.val[beg + e];
-            if (KIND == kExplicitResidual && p.center_opp) x_r -= __ldg(p.Gbias + col_r);
+            if (KIND == kExplicitResidual && p.center_opp) x_r -= __ldg(p.Gbias + (HOT ? (col_r & kHotColMask) : col_r));
         }
     }
 
@@ -398,11 +423,11 @@ template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW> struct Co
                                   KP + (kW * 32 / KP) * KP <= ResidentSmem<T, C, L>::STRIPE;
 };
 
-template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW>
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int TW, bool HOT = false>
 __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, size_t beg, int nnz, T *stripes, const T *gram,
-                                             T *region, int cap, int w, uint32_t tm_addr, int tm_chunks)
+                                             T *region, int cap, int w, uint32_t tm_addr, int tm_chunks, const T *hot = nullptr)
 {
-    typedef ResidentGather<T, C, L, TW == 8 || TW == 1> Gat;   // 2- and 4-warp teams only get rows that fit
+    typedef ResidentGather<T, C, L, TW == 8 || TW == 1, HOT> Gat;   // 2- and 4-warp teams only get rows that fit
     constexpr bool COOP = CoopMode<T, C, L, MODEL, GRAM_SMEM, TW>::value;
     const int team = w / TW, wt = w % TW;
     // one named barrier per (team size, team): a block's teams run ahead of each other by whole slots
@@ -416,6 +441,7 @@ __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, si
         Gat gat(p, region, cap, wt, TW);
         gat.tm_addr = tm_addr;
         gat.tm_chunks = tm_chunks;
+        gat.hot = hot;
         gat.begin(beg, nnz);
         gat.stage();
         if constexpr (COOP) s.solve_coop(row, nnz, gat);
@@ -427,7 +453,7 @@ __device__ __forceinline__ void resident_row(const CgSweepParams &p, int row, si
     team_barrier<TW>(bar_id);   // nobody of the team reuses scratch or regions before everybody is done with the row
 }
 
-template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int MINB = 2>
+template <typename T, int C, int L, int MODEL, bool GRAM_SMEM, int MINB = 2, bool HOT = false>
 __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSweepParams p, const ResidentPlan rp)
 {
     typedef Layout<T, C, L> Lay;
@@ -450,6 +476,24 @@ __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSwee
     const int w = threadIdx.x >> 5;
     T *region = regions + (size_t)w * rp.cap * (Gat::RS + 2);
     Gat(p, region, rp.cap, 0, 1).clear_region();
+    // the table of the most gathered opposing rows, behind the warps' regions (columns >= ldG read as zero)
+    const T *hot = nullptr;
+    if constexpr (HOT) {
+        T *table = regions + (size_t)kW * rp.cap * (Gat::RS + 2);
+        constexpr int U = Gat::KP / Gat::VN;
+        typedef typename VecOf<T>::type Vec;
+        for (int i = threadIdx.x; i < p.n_hot * U; i += blockDim.x) {
+            const int slot = i / U, piece = i % U;
+            Vec v;
+            T *pv = reinterpret_cast<T *>(&v);
+#pragma unroll
+            for (int e2 = 0; e2 < Gat::VN; e2++) pv[e2] = T(0);
+            if (piece * Gat::VN < p.ldG) ldg_vec(p.G + (size_t)p.hot_rows[slot] * (size_t)p.ldG + piece * Gat::VN, pv);
+            *reinterpret_cast<Vec *>(table + (size_t)slot * Gat::KP + piece * Gat::VN) = v;
+        }
+        hot = table;
+        __syncthreads();
+    }
     // tensor-memory tier (see tmem_st8): 256 columns per block, 128 per warp
     __shared__ uint32_t tmem_slot;
     uint32_t tm_addr = 0;
@@ -512,12 +556,12 @@ __global__ void __launch_bounds__(kW * 32, MINB) cg_resident_kernel(const CgSwee
         }
         if (row0 >= 0 || (CoopMode<T, C, L, MODEL, GRAM_SMEM, 1>::value && slot >= rp.s2)) {
             const int nnz = (int)(end0 - beg0);
-            if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
+            if (slot < rp.s8) resident_row<T, C, L, MODEL, GRAM_SMEM, 8, HOT>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks, hot);
 #ifdef CMF_RES_TEAMS   // 2- and 4-warp teams (CMFB200_RES_MODE=0, measured slower): compiled on request only
             else if (slot < rp.s4) resident_row<T, C, L, MODEL, GRAM_SMEM, 4>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
             else if (slot < rp.s2) resident_row<T, C, L, MODEL, GRAM_SMEM, 2>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
 #endif
-            else resident_row<T, C, L, MODEL, GRAM_SMEM, 1>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks);
+            else resident_row<T, C, L, MODEL, GRAM_SMEM, 1, HOT>(p, row0, beg0, nnz, stripes, gram, region, rp.cap, w, tm_addr, tm_chunks, hot);
         }
         row0 = row1;
         beg0 = beg1;
@@ -650,6 +694,18 @@ int launch_cluster(const CgSweepParams &p, int first, int count, int cap, size_t
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// which layouts carry the hot-table variant of the kernel: fp32, 32 < k <= 128, the explicit and the implicit model -- and only
+// in builds made with EXTRA=-DCMF_RES_HOT_ENABLE (then switched on with CMFB200_RES_HOT=1).  Measured at ML10M shape, where the
+// 256 most popular of the 10,677 items hold 19 % of the entries: A sweep 0.957 -> 1.159 ms (128 rows: 1.088): the generic
+// loads, the unpacking and the smaller per-warp cache cost more than a fifth of the gathers served from shared memory saves
+// (profiles/README.md), so the default build leaves it out.
+template <typename T, int C, int L, int MODEL>
+#ifdef CMF_RES_HOT_ENABLE
+constexpr bool kHotCompiled = sizeof(T) == 4 && C == 8 && (L == 8 || L == 16) && MODEL != kModelCollective;
+#else
+constexpr bool kHotCompiled = false;
+#endif
+
 template <typename T, int C, int L, int MODEL, int MINB = 2>
 int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_launches)
 {
@@ -692,7 +748,13 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
                            (mode == 1 ? fixed1 + gram_bytes + 1024 <= per_block : gram_bytes <= per_block / 3);
     if (!gram_smem) gram_bytes = 0;
     if (fixed1 + gram_bytes >= per_block) return 3;
-    int cap1 = (int)((per_block - fixed1 - gram_bytes) / (kW * Gat::kEntryBytes)) & ~7;
+    // the table of hot opposing rows (mode 1, two blocks per SM): taken out of what the per-warp caches would get
+    size_t hot_bytes = 0;
+    if (kHotCompiled<T, C, L, MODEL> && mode == 1 && p.hot_idx && p.hot_rows && p.n_hot > 0) {
+        hot_bytes = (size_t)p.n_hot * Lay::KP * sizeof(T);
+        if (fixed1 + gram_bytes + hot_bytes + 1024 > per_block) hot_bytes = 0;
+    }
+    int cap1 = (int)((per_block - fixed1 - gram_bytes - hot_bytes) / (kW * Gat::kEntryBytes)) & ~7;
     const size_t fixedC = (size_t)(Scr::elems() + 2 * Scr::RED_STRIDE) * sizeof(T);
     int capC = (int)((per_block - fixedC) / (kW * Gat::kEntryBytes)) & ~7;
     if (mode != 1 && (cap1 < 8 || capC < 8)) return 3;   // teams need whole rows resident
@@ -759,8 +821,12 @@ int launch_resident_cfg(const CgSweepParams &p, cudaStream_t stream, int *n_laun
         if (n_launches) (*n_launches)++;
     }
     if (rp.n_slots > 0) {
-        const size_t smem1 = fixed1 + gram_bytes + (size_t)kW * cap1 * Gat::kEntryBytes;
+        const size_t smem1 = fixed1 + gram_bytes + (size_t)kW * cap1 * Gat::kEntryBytes + hot_bytes;
         auto kern = gram_smem ? cg_resident_kernel<T, C, L, MODEL, true, MINB> : cg_resident_kernel<T, C, L, MODEL, false, MINB>;
+        if constexpr (kHotCompiled<T, C, L, MODEL>) {
+            if (hot_bytes)
+                kern = gram_smem ? cg_resident_kernel<T, C, L, MODEL, true, MINB, true> : cg_resident_kernel<T, C, L, MODEL, false, MINB, true>;
+        }
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess) return 1;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kW * 32, smem1);
